@@ -1,0 +1,403 @@
+// fft_kernels.cuh -- shared-memory-staged mixed-radix Stockham line transforms.
+//
+// One thread block transforms LPB lines of N = 2^LG_N complex points.  A line is
+// owned by TT = N/E threads; each thread keeps E = 2^LG_E points in registers
+// (x[t + c*TT], c < E) and the stages are
+//
+//     radix-E, radix-E, ..., radix-(N / E^k)        (greedy, big radices first)
+//
+// Stage s (sub-transform length NS = E^s before it) does, for butterfly j:
+//     k = j mod NS;  in_m = x[j + m*N/R] * W_{NS*R}^{k m};  DFT-R;
+//     y[(j-k)*R + k + p*NS] = out_p
+// which is the Stockham auto-sort recurrence: reads are always x[t + c*TT]
+// (conflict-free, coalesced when they come from HBM), the scatter goes through
+// shared memory, and after the LAST stage the outputs are again at t + c*TT so
+// they leave for HBM coalesced.  HBM traffic is one read and one write of the
+// line; twiddles come from small per-stage tables (plan.cu) that stay in L1/L2.
+//
+// What the reference does per line instead (all fused here):
+//   gather + cast + zero-pad/crop   /root/reference/dsc/src/dsc.cpp:1981-1994
+//   log2(N) radix-2 levels          /root/reference/dsc/include/dsc_fft.h:57-103
+//   1/N on the inverse              /root/reference/dsc/include/dsc_fft.h:168-175
+//   real post/pre-processing        /root/reference/dsc/include/dsc_fft.h:199-237
+//   scatter                         /root/reference/dsc/src/dsc.cpp:1998-2003
+#pragma once
+
+#include "fft_math.cuh"
+
+namespace dscfft {
+
+enum Mode : int {
+    MODE_C2C = 0,   // complex / real-cast / real-pair / staged-row input -> complex out
+    MODE_R2C = 1,   // rfft : 2N reals -> N+1 bins, un-mixing fused after the last stage
+    MODE_C2R = 2,   // irfft: N+1 bins -> 2N reals, mixing fused before the first stage
+};
+
+// how MODE_C2C reads its input
+enum InKind : int {
+    IN_COMPLEX = 0,  // cx<T> elements, straight into registers
+    IN_REAL = 1,     // T elements, imag = 0 (cast_op, /root/reference/dsc/include/dsc_ops.h:12-23)
+    IN_PAIRS = 2,    // two T elements pstride apart form one complex (packed real transform)
+    IN_ROWS = 3,     // cx<T> rows, loaded cooperatively through shared memory
+};
+
+// Geometry of one launch.  A "line" index L decomposes as (o, in) = (L / inner, L % inner);
+// element i of the line sits at   o*ostride + in*lstride + i*estride   (in elements of the
+// respective dtype).  For an (outer, n, inner) tensor: ostride = n*inner, lstride = 1,
+// estride = inner -- the reference's dsc_axis_iterator order, dsc_iter.h:19-47.
+struct LineGeom {
+    long long ostride, lstride, estride;
+};
+
+struct FftArgs {
+    const void *x;
+    void *out;
+    long long lines;
+    long long inner;
+    LineGeom gi, go;
+    long long in_limit;   // element (i, in) is read iff i*gi.estride + in*gi.lstride < in_limit, else 0
+    const void *tw[5];    // tw[s]: stage-s table, (R_s - 1) x NS_s forward twiddles, [m-1][k]
+    const void *tw_real;  // W_{2N}^k, k <= N/2            (MODE_R2C / MODE_C2R)
+    const void *tw_lo;    // four-step: W_M^p,        p <  2^four_shift
+    const void *tw_hi;    // four-step: W_M^(p << four_shift)
+    int four_shift;       // 0 = no inter-pass twiddle
+    int four_mask;
+    long long gi_pstride; // IN_PAIRS / MODE_R2C: distance between the two reals of a pair
+    long long go_pstride; // MODE_C2R: same, for the output
+    int in_kind;          // InKind (MODE_C2C only)
+    int strided;          // thread mapping: 1 = adjacent lines on adjacent lanes
+    double scale;         // applied to the outputs when do_scale (1/N of the inverse)
+    int do_scale;
+};
+
+template <int LG_N, int LG_E> struct Sched {
+    static constexpr int N = 1 << LG_N;
+    static constexpr int E = 1 << LG_E;
+    static constexpr int TT = N / E;
+    static constexpr int STAGES = LG_E == 0 ? 1 : (LG_N + LG_E - 1) / LG_E;
+    static constexpr int lg_r(int s) { return (LG_N - s * LG_E) < LG_E ? (LG_N - s * LG_E) : LG_E; }
+    // padded length of one line in shared memory (+1 keeps adjacent lines on different banks)
+    static constexpr int LINE = N + (N >> LG_E) + 1;
+    static DSC_DEV int pad(int i) { return i + (i >> LG_E); }
+    static_assert(STAGES <= 5, "FftArgs::tw / dsc_cuda_plan::tw1 hold 5 stage tables");
+};
+
+template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
+    using Sc = Sched<LG_N, LG_E>;
+    using V = cx<T>;
+    static constexpr int E = Sc::E, TT = Sc::TT;
+    static constexpr int LG_R = Sc::lg_r(S), R = 1 << LG_R, NB = E / R;
+    static constexpr int LG_NS = S * LG_E, NS = 1 << LG_NS;
+    static constexpr bool LAST = (S == Sc::STAGES - 1);
+
+    static DSC_DEV void run(V (&v)[E], V *sm, const int t, const FftArgs &a, const bool block_sync) {
+        const V *__restrict__ tw = (const V *)a.tw[S];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = t + b * TT;
+            const int k = j & (NS - 1);
+            V r[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) r[m] = v[b + m * NB];
+            if constexpr (S > 0) {
+#pragma unroll
+                for (int m = 1; m < R; ++m) r[m] = cmul_tw<FWD>(r[m], __ldg(tw + (m - 1) * NS + k));
+            }
+            Dft<R, FWD, T>::run(r);
+            if constexpr (LAST) {
+#pragma unroll
+                for (int p = 0; p < R; ++p) v[b + p * NB] = r[p];
+            } else {
+                const int base = ((j - k) << LG_R) + k;
+#pragma unroll
+                for (int p = 0; p < R; ++p) sm[Sc::pad(base + p * NS)] = r[p];
+            }
+        }
+        if constexpr (!LAST) {
+            if (block_sync) __syncthreads(); else __syncwarp();
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad(t + c * TT)];
+            if (block_sync) __syncthreads(); else __syncwarp();
+            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm, t, a, block_sync);
+        }
+    }
+};
+
+template <typename T> DSC_DEV cx<T> four_step_twiddle(const FftArgs &a, const long long p) {
+    const cx<T> lo = __ldg((const cx<T> *)a.tw_lo + (int)(p & a.four_mask));
+    const cx<T> hi = __ldg((const cx<T> *)a.tw_hi + (int)(p >> a.four_shift));
+    return cmul(lo, hi);
+}
+
+// Un-mix / mix step of the packed real transform for one bin pair (k, N-k).
+// Forward (dsc_fft.h:199-214 with c = -1/2, w = W_2N^k):   X[k], X[N-k] from Z[k], Z[N-k].
+// Inverse (same lines with c = +1/2, w = conj W_2N^k):     z[k], z[N-k] from X[k], X[N-k].
+template <bool FWD, typename T>
+DSC_DEV void real_pair(const cx<T> a, const cx<T> b, const cx<T> w_fwd, cx<T> &ra, cx<T> &rb) {
+    const T h1r = (T)0.5 * (a.x + b.x), h1i = (T)0.5 * (a.y - b.y);
+    const T c = FWD ? (T)-0.5 : (T)0.5;
+    const T h2r = -c * (a.y + b.y), h2i = c * (a.x - b.x);
+    const T wr = w_fwd.x, wi = FWD ? w_fwd.y : -w_fwd.y;
+    ra = mk<T>(h1r + wr * h2r - wi * h2i,  h1i + wr * h2i + wi * h2r);
+    rb = mk<T>(h1r - wr * h2r + wi * h2i, -h1i + wr * h2i + wi * h2r);
+}
+
+// THREADS = LPB * TT.  Dynamic shared memory: LPB * Sched::LINE * sizeof(cx<T>).
+template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
+__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)))
+fft_lines(const FftArgs a) {
+    using Sc = Sched<LG_N, LG_E>;
+    using V = cx<T>;
+    constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, THREADS = LPB * TT;
+    constexpr int PAIRS = E > 1 ? E / 2 : 1;   // bin pairs per thread in the real modes
+    DSC_DYN_SMEM(smem_raw);
+    V *sm_all = (V *)smem_raw;
+
+    const int tid = threadIdx.x;
+    int l, t;
+    if (a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
+    V *sm = sm_all + l * Sc::LINE;
+    // warp-level barriers suffice only when every line lives inside one warp
+    const bool block_sync = a.strided || TT > 32;
+
+    const long long line = (long long)blockIdx.x * LPB + l;
+    const bool active = line < a.lines;
+    const long long o = active ? line / a.inner : 0;
+    const long long in = active ? line % a.inner : 0;
+    const long long ibase = o * a.gi.ostride + in * a.gi.lstride;
+    const long long obase = o * a.go.ostride + in * a.go.lstride;
+    const long long lim = active ? a.in_limit - in * a.gi.lstride : 0;   // read iff offset < lim
+    const V zero = mk<T>((T)0, (T)0);
+
+    V v[E];
+
+    // ---------------------------------------------------------------- load
+    if (MODE == MODE_C2R) {
+        // bins X[0..N] -> packed z[0..N); DC/Nyquist use real parts only (dsc_fft.h:227-228)
+        const V *__restrict__ xc = (const V *)a.x + ibase;
+        const V *__restrict__ twr = (const V *)a.tw_real;
+        auto bin = [&](int i) -> V {
+            const long long off = (long long)i * a.gi.estride;
+            return off < lim ? xc[off] : zero;
+        };
+#pragma unroll
+        for (int c = 0; c < PAIRS; ++c) {
+            const int k = t + c * TT;
+            if (c == 0 && k == 0) {
+                const V x0 = bin(0), xn = bin(N);
+                sm[Sc::pad(0)] = mk<T>((T)0.5 * (x0.x + xn.x), (T)0.5 * (x0.x - xn.x));
+                if (N >= 2) { const V xh = bin(N / 2); sm[Sc::pad(N / 2)] = mk<T>(xh.x, -xh.y); }
+            } else if (k < N / 2) {
+                V za, zb;
+                real_pair<false, T>(bin(k), bin(N - k), __ldg(twr + k), za, zb);
+                sm[Sc::pad(k)] = za;
+                sm[Sc::pad(N - k)] = zb;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad(t + c * TT)];
+        __syncthreads();
+    } else if (MODE == MODE_R2C || a.in_kind == IN_PAIRS) {
+        // 2N reals seen as N complex: z[j] = (x[..2j], x[..2j+1]); gi is in REAL elements
+        const T *__restrict__ xr = (const T *)a.x + ibase;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const long long off = (long long)(t + c * TT) * a.gi.estride;
+            const T re = off < lim ? xr[off] : (T)0;
+            const T im = off + a.gi_pstride < lim ? xr[off + a.gi_pstride] : (T)0;
+            v[c] = mk<T>(re, im);
+        }
+    } else if (a.in_kind == IN_REAL) {
+        const T *__restrict__ xr = (const T *)a.x + ibase;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const long long off = (long long)(t + c * TT) * a.gi.estride;
+            v[c] = mk<T>(off < lim ? xr[off] : (T)0, (T)0);
+        }
+    } else if (a.in_kind == IN_COMPLEX) {
+        const V *__restrict__ xc = (const V *)a.x + ibase;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const long long off = (long long)(t + c * TT) * a.gi.estride;
+            v[c] = off < lim ? xc[off] : zero;
+        }
+    } else {  // IN_ROWS: LPB rows loaded cooperatively (coalesced along the row), then picked up per line
+        const long long line0 = (long long)blockIdx.x * LPB;
+        for (int e = tid; e < LPB * N; e += THREADS) {
+            const int row = e / N, pos = e % N;
+            const long long rl = line0 + row;
+            V val = zero;
+            if (rl < a.lines) {
+                const long long ro = rl / a.inner, rin = rl % a.inner;
+                val = ((const V *)a.x)[ro * a.gi.ostride + rin * a.gi.lstride + (long long)pos * a.gi.estride];
+            }
+            sm_all[row * Sc::LINE + Sc::pad(pos)] = val;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad(t + c * TT)];
+        __syncthreads();
+    }
+
+    // ---------------------------------------------------------------- transform
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, t, a, block_sync);
+
+    if (a.do_scale) {
+        const T s = (T)a.scale;
+#pragma unroll
+        for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
+    }
+
+    // ---------------------------------------------------------------- store
+    if (MODE == MODE_C2C) {
+        if (a.four_shift) {   // four-step first pass: times W_M^(in * k1)
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                v[c] = cmul_tw<FWD>(v[c], four_step_twiddle<T>(a, in * (long long)(t + c * TT)));
+        }
+        if (active) {
+            V *__restrict__ oc = (V *)a.out + obase;
+#pragma unroll
+            for (int c = 0; c < E; ++c) oc[(long long)(t + c * TT) * a.go.estride] = v[c];
+        }
+    } else if (MODE == MODE_C2R) {
+        // N complex = 2N reals; go is in REAL elements
+        if (active) {
+            T *__restrict__ orl = (T *)a.out + obase;
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const long long off = (long long)(t + c * TT) * a.go.estride;
+                orl[off] = v[c].x;
+                orl[off + a.go_pstride] = v[c].y;
+            }
+        }
+    } else {  // MODE_R2C: Z -> shared memory, then each thread un-mixes its bin pairs
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < E; ++c) sm[Sc::pad(t + c * TT)] = v[c];
+        __syncthreads();
+        if (active) {
+            V *__restrict__ oc = (V *)a.out + obase;
+            const V *__restrict__ twr = (const V *)a.tw_real;
+#pragma unroll
+            for (int c = 0; c < PAIRS; ++c) {
+                const int k = t + c * TT;
+                if (c == 0 && k == 0) {
+                    // DC and Nyquist come from Z[0] alone, imag exactly 0 (dsc_fft.h:220-225)
+                    const V z0 = sm[Sc::pad(0)];
+                    oc[0] = mk<T>(z0.x + z0.y, (T)0);
+                    oc[(long long)N * a.go.estride] = mk<T>(z0.x - z0.y, (T)0);
+                    if (N >= 2) {
+                        const V zh = sm[Sc::pad(N / 2)];
+                        oc[(long long)(N / 2) * a.go.estride] = mk<T>(zh.x, -zh.y);
+                    }
+                } else if (k < N / 2) {
+                    V xa, xb;
+                    real_pair<true, T>(sm[Sc::pad(k)], sm[Sc::pad(N - k)], __ldg(twr + k), xa, xb);
+                    oc[(long long)k * a.go.estride] = xa;
+                    oc[(long long)(N - k) * a.go.estride] = xb;
+                }
+            }
+        }
+    }
+}
+
+// Large packed-real transforms (order N beyond one shared-memory pass): the same bin-pair
+// step as a standalone elementwise kernel.
+//   FWD : rows of N+1 bins hold Z[0..N) (slot N unused); rewritten in place to X[0..N].
+//   !FWD: bins x (row stride x_ostride, `take` valid bins) -> packed z rows of N in `z`.
+template <bool FWD, typename T>
+__global__ void real_mix_rows(const cx<T> *__restrict__ x, cx<T> *__restrict__ z,
+                              long long rows, int n, long long x_ostride, int take,
+                              const cx<T> *__restrict__ tw_lo, const cx<T> *__restrict__ tw_hi,
+                              int shift, int mask) {
+    using V = cx<T>;
+    const int half = n / 2;                 // work items per row: k = 0 .. half-1 (k = 0 also does n/2, n)
+    const long long total = rows * (long long)half;
+    const V zero = mk<T>((T)0, (T)0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / half;
+        const int k = (int)(i % half);
+        if (FWD) {
+            V *zr = z + row * (long long)(n + 1);
+            if (k == 0) {
+                const V z0 = zr[0];
+                zr[0] = mk<T>(z0.x + z0.y, (T)0);
+                zr[n] = mk<T>(z0.x - z0.y, (T)0);
+                const V zh = zr[half];
+                zr[half] = mk<T>(zh.x, -zh.y);
+            } else {
+                // W_2N^k through the same two-table split as the four-step twiddle
+                const V w = cmul(__ldg(tw_lo + (k & mask)), __ldg(tw_hi + (k >> shift)));
+                V xa, xb;
+                real_pair<true, T>(zr[k], zr[n - k], w, xa, xb);
+                zr[k] = xa;
+                zr[n - k] = xb;
+            }
+        } else {
+            const V *xr = x + row * x_ostride;
+            V *zr = z + row * (long long)n;
+            auto bin = [&](int j) -> V { return j < take ? xr[j] : zero; };
+            if (k == 0) {
+                const V x0 = bin(0), xn = bin(n), xh = bin(half);
+                zr[0] = mk<T>((T)0.5 * (x0.x + xn.x), (T)0.5 * (x0.x - xn.x));
+                zr[half] = mk<T>(xh.x, -xh.y);
+            } else {
+                const V w = cmul(__ldg(tw_lo + (k & mask)), __ldg(tw_hi + (k >> shift)));
+                V za, zb;
+                real_pair<false, T>(bin(k), bin(n - k), w, za, zb);
+                zr[k] = za;
+                zr[n - k] = zb;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Twiddle tables, computed on the device in double and rounded once to T
+// (the reference evaluates cos/sin in T, dsc_fft.h:42-49; see plan.cu).
+
+// stage table: out[(m-1)*NS + k] = exp(-2 pi i k m / (NS*R)),  m in [1,R), k in [0,NS)
+template <typename T>
+__global__ void fill_stage_twiddles(cx<T> *out, int ns, int r) {
+    const int total = (r - 1) * ns;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int m = i / ns + 1, k = i % ns;
+        // angle = -2 pi (k m) / (ns r): reduce the integer product first, exactly
+        const long long num = ((long long)k * m) % ((long long)ns * r);
+        double s, c;
+        sincospi(-2.0 * (double)num / (double)((long long)ns * r), &s, &c);
+        out[i] = mk<T>((T)c, (T)s);
+    }
+}
+
+// out[k] = exp(-2 pi i (k * mult) / denom), k in [0,count)
+template <typename T>
+__global__ void fill_power_twiddles(cx<T> *out, long long count, long long mult, long long denom) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long num = (i * mult) % denom;
+        double s, c;
+        sincospi(-2.0 * (double)num / (double)denom, &s, &c);
+        out[i] = mk<T>((T)c, (T)s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Frequency-domain pointwise product (mul_op, /root/reference/dsc/include/dsc_ops.h:68-78),
+// b broadcast over rows when b_rows == 0.
+template <typename T>
+__global__ void cmul_rows(const cx<T> *__restrict__ a, const cx<T> *__restrict__ b, cx<T> *__restrict__ out,
+                          long long rows, long long cols, int b_rows) {
+    const long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const cx<T> x = a[i];
+        const cx<T> y = b_rows ? b[i] : b[i % cols];
+        out[i] = mk<T>(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+    }
+}
+
+}  // namespace dscfft

@@ -1,0 +1,447 @@
+// fft_launch.cu -- the extern "C" launch layer declared in include/dsc_cuda.h:
+// plan construction (radix schedule + twiddle tables in HBM) and the launch logic that
+// maps (outer, n, inner) tensors onto fft_lines<> grids, single-pass or four-step.
+//
+// No cudaMalloc / cudaFree anywhere in this file: plan and work memory belong to the caller.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "dsc_cuda.h"
+#include "fft_dispatch.cuh"
+
+using namespace dscfft;
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#if defined(DSC_EMUL)
+#define DSC_LAUNCH(fn, grid, block, smem, stream, ...) dsc_emul::launch(grid, block, smem, [=]() { fn(__VA_ARGS__); })
+inline int check_launch(const char *) { return 0; }
+#else
+#define DSC_LAUNCH(fn, grid, block, smem, stream, ...) fn<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+inline int check_launch(const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+#endif
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
+
+template <typename T> constexpr int dtype_of();
+template <> constexpr int dtype_of<float>() { return DSC_CUDA_F32; }
+template <> constexpr int dtype_of<double>() { return DSC_CUDA_F64; }
+
+// ---- plan geometry -------------------------------------------------------------------
+
+struct SubSched {           // stage layout of one shared-memory pass of length 2^lg
+    int stages;
+    int ns[DSC_CUDA_MAX_STAGES], r[DSC_CUDA_MAX_STAGES];
+};
+
+SubSched sub_sched(int lg, int lg_e_max) {
+    SubSched s{};
+    const int lg_e = lg < lg_e_max ? lg : lg_e_max;
+    s.stages = lg_e == 0 ? 1 : (lg + lg_e - 1) / lg_e;
+    for (int i = 0; i < s.stages; ++i) {
+        const int rem = lg - i * lg_e;
+        s.r[i] = 1 << (rem < lg_e ? rem : lg_e);
+        s.ns[i] = 1 << (i * lg_e);
+    }
+    return s;
+}
+
+struct PlanLayout {
+    int lg_n, lg_n1, lg_n2, four_shift, real_shift;
+    size_t off_tw1[DSC_CUDA_MAX_STAGES], off_tw2[DSC_CUDA_MAX_STAGES];
+    size_t off_lo, off_hi, off_real, off_real_lo, off_real_hi, total;
+    bool ok;
+};
+
+template <typename T> PlanLayout plan_layout(int n, int fft_type) {
+    PlanLayout L{};
+    const size_t es = sizeof(cx<T>);
+    L.lg_n = ilog2(n);
+    if (L.lg_n <= Tile<T>::MAX_LG) { L.lg_n1 = L.lg_n; L.lg_n2 = 0; }
+    else {
+        L.lg_n2 = L.lg_n / 2 < 10 ? L.lg_n / 2 : 10;   // rows pass: <= 1024 points
+        L.lg_n1 = L.lg_n - L.lg_n2;
+    }
+    L.ok = L.lg_n1 <= Tile<T>::MAX_LG;
+    size_t off = 0;
+    auto take = [&](size_t count) { const size_t o = off; off = align_up(off + count * es, 256); return o; };
+    const SubSched s1 = sub_sched(L.lg_n1, Tile<T>::LG_E);
+    for (int s = 1; s < s1.stages; ++s) L.off_tw1[s] = take((size_t)(s1.r[s] - 1) * s1.ns[s]);
+    if (L.lg_n2) {
+        const SubSched s2 = sub_sched(L.lg_n2, Tile<T>::LG_E);
+        for (int s = 1; s < s2.stages; ++s) L.off_tw2[s] = take((size_t)(s2.r[s] - 1) * s2.ns[s]);
+        L.four_shift = (L.lg_n + 1) / 2;
+        L.off_lo = take((size_t)1 << L.four_shift);
+        L.off_hi = take((size_t)1 << (L.lg_n - L.four_shift));
+    }
+    if (fft_type == DSC_CUDA_FFT_REAL) {
+        if (L.lg_n2 == 0) L.off_real = take((size_t)n / 2 + 1);
+        else {
+            // W_2n^k for k < n/2: index has lg_n - 1 bits
+            L.real_shift = L.lg_n / 2;
+            L.off_real_lo = take((size_t)1 << L.real_shift);
+            L.off_real_hi = take(((size_t)n / 2 >> L.real_shift) + 1);
+        }
+    }
+    L.total = off ? off : 256;
+    return L;
+}
+
+template <typename T>
+int build_tables(dsc_cuda_plan *p, const PlanLayout &L, void *stream) {
+    using V = cx<T>;
+    char *base = (char *)p->dev_base;
+    const int n = p->n;
+    auto fill_stage = [&](void *dst, int ns, int r) {
+        const int total = (r - 1) * ns;
+        DSC_LAUNCH(fill_stage_twiddles<T>, (total + 255) / 256, 256, 0, stream, (V *)dst, ns, r);
+    };
+    auto fill_pow = [&](void *dst, long long count, long long mult, long long denom) {
+        const int blocks = (int)((count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024);
+        DSC_LAUNCH(fill_power_twiddles<T>, blocks, 256, 0, stream, (V *)dst, count, mult, denom);
+    };
+    const SubSched s1 = sub_sched(L.lg_n1, Tile<T>::LG_E);
+    for (int s = 1; s < s1.stages; ++s) {
+        p->tw1[s] = base + L.off_tw1[s];
+        fill_stage(p->tw1[s], s1.ns[s], s1.r[s]);
+    }
+    if (L.lg_n2) {
+        const SubSched s2 = sub_sched(L.lg_n2, Tile<T>::LG_E);
+        for (int s = 1; s < s2.stages; ++s) {
+            p->tw2[s] = base + L.off_tw2[s];
+            fill_stage(p->tw2[s], s2.ns[s], s2.r[s]);
+        }
+        p->tw_lo = base + L.off_lo;
+        p->tw_hi = base + L.off_hi;
+        fill_pow(p->tw_lo, 1LL << L.four_shift, 1, n);
+        fill_pow(p->tw_hi, 1LL << (L.lg_n - L.four_shift), 1LL << L.four_shift, n);
+    }
+    if (p->fft_type == DSC_CUDA_FFT_REAL) {
+        if (L.lg_n2 == 0) {
+            p->tw_real = base + L.off_real;
+            fill_pow(p->tw_real, n / 2 + 1, 1, 2LL * n);
+        } else {
+            p->tw_real_lo = base + L.off_real_lo;
+            p->tw_real_hi = base + L.off_real_hi;
+            fill_pow(p->tw_real_lo, 1LL << L.real_shift, 1, 2LL * n);
+            fill_pow(p->tw_real_hi, ((long long)n / 2 >> L.real_shift) + 1, 1LL << L.real_shift, 2LL * n);
+        }
+    }
+    return check_launch("twiddle tables");
+}
+
+// ---- launches --------------------------------------------------------------------------
+
+int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a, void *stream) {
+    KernelEntry &e = table[lg_n];
+#if !defined(DSC_EMUL)
+    if (!e.configured) {
+        if (e.smem > 48 * 1024) {
+            const cudaError_t err = cudaFuncSetAttribute((const void *)e.fn,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, e.smem);
+            if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
+        }
+        e.configured = true;
+    }
+#endif
+    if (a.lines <= 0) return 0;
+    const long long blocks = (a.lines + e.lpb - 1) / e.lpb;
+    if (blocks > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "too many lines for one grid: %lld", a.lines);
+    DSC_LAUNCH(e.fn, (unsigned)blocks, e.threads, e.smem, stream, a);
+    return check_launch("fft_lines");
+}
+
+template <typename T>
+void set_stage_tables(FftArgs &a, void *const tw[DSC_CUDA_MAX_STAGES]) {
+    for (int s = 0; s < DSC_CUDA_MAX_STAGES; ++s) a.tw[s] = tw[s];
+}
+
+template <typename T, bool FWD>
+KernelEntry *c2c_table(bool strided_shape) {
+    return strided_shape ? get_table<T, FWD, MODE_C2C, true>() : get_table<T, FWD, MODE_C2C, false>();
+}
+
+// The two passes of the four-step decomposition n = n1*n2 of `rows` contiguous lines:
+//   A: for every n2, length-n1 transform over stride-n2 data, times W_n^(n2 k1) -> work[row][k1][n2]
+//   B: for every k1, length-n2 transform of the contiguous run work[row][k1][:] -> dst[row][k1 + n1 k2]
+// `src` geometry (element kind, row stride, limit) comes in through `first`.
+template <typename T, bool FWD>
+int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
+              void *dst, long long dst_row_stride, bool scale, void *stream) {
+    const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
+    // pass A
+    FftArgs a = first;
+    a.out = work;
+    a.lines = rows * n2;
+    a.inner = n2;
+    a.go = LineGeom{n, 1, n2};
+    set_stage_tables<T>(a, p->tw1);
+    a.tw_lo = p->tw_lo; a.tw_hi = p->tw_hi;
+    a.four_shift = p->four_shift; a.four_mask = (1 << p->four_shift) - 1;
+    a.strided = 1;
+    a.do_scale = 0;
+    int rc = launch_lines(c2c_table<T, FWD>(true), p->lg_n1, a, stream);
+    if (rc) return rc;
+    // pass B
+    FftArgs b{};
+    b.x = work; b.out = dst;
+    b.lines = rows * n1;
+    b.inner = n1;
+    b.gi = LineGeom{n, n2, 1};
+    b.go = LineGeom{dst_row_stride, 1, n1};
+    b.in_limit = 0;
+    b.in_kind = IN_ROWS;
+    set_stage_tables<T>(b, p->tw2);
+    b.strided = 1;
+    b.do_scale = scale; b.scale = 1.0 / (double)n;
+    return launch_lines(c2c_table<T, FWD>(true), p->lg_n2, b, stream);
+}
+
+template <typename T, bool FWD>
+int run_fft(const dsc_cuda_plan *p, const void *x, bool x_real, void *out,
+            long long outer, int x_n, long long inner, void *work, size_t work_bytes, void *stream) {
+    const long long n = p->n;
+    const long long take = x_n < n ? x_n : n;
+    if (p->lg_n2 == 0) {
+        FftArgs a{};
+        a.x = x; a.out = out;
+        a.lines = outer * inner;
+        a.inner = inner;
+        a.gi = LineGeom{(long long)x_n * inner, 1, inner};
+        a.go = LineGeom{n * inner, 1, inner};
+        a.in_limit = take * inner;
+        a.in_kind = x_real ? IN_REAL : IN_COMPLEX;
+        set_stage_tables<T>(a, p->tw1);
+        a.strided = inner > 1;
+        a.do_scale = !FWD; a.scale = 1.0 / (double)n;
+        return launch_lines(c2c_table<T, FWD>(inner > 1), p->lg_n, a, stream);
+    }
+    if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis", n);
+    const size_t row_bytes = (size_t)n * sizeof(cx<T>);
+    if (!work || work_bytes < row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (n=%lld)", n);
+    const long long chunk = (long long)(work_bytes / row_bytes);
+    for (long long r0 = 0; r0 < outer; r0 += chunk) {
+        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
+        FftArgs a{};
+        const size_t in_es = x_real ? sizeof(T) : sizeof(cx<T>);
+        a.x = (const char *)x + (size_t)r0 * x_n * in_es;
+        a.gi = LineGeom{(long long)x_n, 1, 1LL << p->lg_n2};
+        a.in_limit = take;
+        a.in_kind = x_real ? IN_REAL : IN_COMPLEX;
+        const int rc = four_step<T, FWD>(p, a, rows, work, (char *)out + (size_t)r0 * row_bytes, n, !FWD, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+template <typename T>
+int run_rfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, int x_n, long long inner,
+             void *work, size_t work_bytes, void *stream) {
+    using V = cx<T>;
+    const long long n = p->n;                       // complex order; 2n real samples
+    const long long take = x_n < 2 * n ? x_n : 2 * n;
+    if (p->lg_n2 == 0) {
+        FftArgs a{};
+        a.x = x; a.out = out;
+        a.lines = outer * inner;
+        a.inner = inner;
+        a.gi = LineGeom{(long long)x_n * inner, 1, 2 * inner};   // REAL elements
+        a.gi_pstride = inner;
+        a.go = LineGeom{(n + 1) * inner, 1, inner};
+        a.in_limit = take * inner;
+        set_stage_tables<T>(a, p->tw1);
+        a.tw_real = p->tw_real;
+        a.strided = inner > 1;
+        return launch_lines(get_table<T, true, MODE_R2C, false>(), p->lg_n, a, stream);
+    }
+    if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass rfft (order %lld) along a strided axis", n);
+    const size_t row_bytes = (size_t)n * sizeof(V);
+    if (!work || work_bytes < row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
+    const long long chunk = (long long)(work_bytes / row_bytes);
+    for (long long r0 = 0; r0 < outer; r0 += chunk) {
+        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
+        FftArgs a{};
+        a.x = (const T *)x + (size_t)r0 * x_n;
+        a.gi = LineGeom{(long long)x_n, 2, 2LL << p->lg_n2};     // REAL elements
+        a.gi_pstride = 1;
+        a.in_limit = take;
+        a.in_kind = IN_PAIRS;
+        V *dst = (V *)out + (size_t)r0 * (n + 1);
+        int rc = four_step<T, true>(p, a, rows, work, dst, n + 1, false, stream);
+        if (rc) return rc;
+        const long long items = rows * (n / 2);
+        const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+        auto mix = real_mix_rows<true, T>;
+        DSC_LAUNCH(mix, blocks, 256, 0, stream, (const V *)nullptr, dst, rows, (int)n,
+                   (long long)0, 0, (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift,
+                   (1 << p->real_shift) - 1);
+        rc = check_launch("real_mix_rows");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+template <typename T>
+int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, int x_n, long long inner,
+              void *work, size_t work_bytes, void *stream) {
+    using V = cx<T>;
+    const long long n = p->n;
+    const long long take = x_n < n + 1 ? x_n : n + 1;
+    if (p->lg_n2 == 0) {
+        FftArgs a{};
+        a.x = x; a.out = out;
+        a.lines = outer * inner;
+        a.inner = inner;
+        a.gi = LineGeom{(long long)x_n * inner, 1, inner};
+        a.go = LineGeom{2 * n * inner, 1, 2 * inner};            // REAL elements
+        a.go_pstride = inner;
+        a.in_limit = take * inner;
+        set_stage_tables<T>(a, p->tw1);
+        a.tw_real = p->tw_real;
+        a.strided = inner > 1;
+        a.do_scale = 1; a.scale = 1.0 / (double)n;               // 2/(2n), dsc_fft.h:232
+        return launch_lines(get_table<T, false, MODE_C2R, false>(), p->lg_n, a, stream);
+    }
+    if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass irfft (order %lld) along a strided axis", n);
+    // work = [ packed z rows | four-step intermediate ], both rows x n complex
+    const size_t row_bytes = (size_t)n * sizeof(V);
+    if (!work || work_bytes < 2 * row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
+    const long long chunk = (long long)(work_bytes / (2 * row_bytes));
+    for (long long r0 = 0; r0 < outer; r0 += chunk) {
+        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
+        V *z = (V *)work;
+        V *mid = z + (size_t)rows * n;
+        const long long items = rows * (n / 2);
+        const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+        auto mix = real_mix_rows<false, T>;
+        DSC_LAUNCH(mix, blocks, 256, 0, stream, (const V *)x + (size_t)r0 * x_n, z, rows,
+                   (int)n, (long long)x_n, (int)take, (const V *)p->tw_real_lo, (const V *)p->tw_real_hi,
+                   p->real_shift, (1 << p->real_shift) - 1);
+        int rc = check_launch("real_mix_rows");
+        if (rc) return rc;
+        FftArgs a{};
+        a.x = z;
+        a.gi = LineGeom{n, 1, 1LL << p->lg_n2};
+        a.in_limit = n;
+        a.in_kind = IN_COMPLEX;
+        rc = four_step<T, false>(p, a, rows, mid, (V *)out + (size_t)r0 * n, n, true, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+bool plan_ok(const dsc_cuda_plan *p) {
+    return p && p->n >= 1 && (p->dtype == DSC_CUDA_F32 || p->dtype == DSC_CUDA_F64);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+
+extern "C" {
+
+const char *dsc_cuda_last_error(void) { return g_err; }
+
+int dsc_cuda_device_count(void) {
+#if defined(DSC_EMUL)
+    return 1;
+#else
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+#endif
+}
+
+size_t dsc_cuda_plan_bytes(int n, int fft_type, int dtype) {
+    if (n < 1 || (n & (n - 1))) return 0;
+    const PlanLayout L = dtype == DSC_CUDA_F64 ? plan_layout<double>(n, fft_type) : plan_layout<float>(n, fft_type);
+    return L.ok ? L.total : 0;
+}
+
+int dsc_cuda_plan_build(dsc_cuda_plan *plan, int n, int fft_type, int dtype,
+                        void *dev_mem, size_t dev_bytes, void *stream) {
+    if (!plan || n < 1 || (n & (n - 1))) return fail(DSC_CUDA_EINVAL, "plan length %d is not a power of two", n);
+    if (dtype != DSC_CUDA_F32 && dtype != DSC_CUDA_F64) return fail(DSC_CUDA_EINVAL, "plan dtype %d", dtype);
+    if (fft_type != DSC_CUDA_FFT_REAL && fft_type != DSC_CUDA_FFT_COMPLEX) return fail(DSC_CUDA_EINVAL, "plan type %d", fft_type);
+    const PlanLayout L = dtype == DSC_CUDA_F64 ? plan_layout<double>(n, fft_type) : plan_layout<float>(n, fft_type);
+    if (!L.ok) return fail(DSC_CUDA_EUNSUPPORTED, "length 2^%d exceeds the two-pass range", L.lg_n);
+    if (!dev_mem || dev_bytes < L.total) return fail(DSC_CUDA_ENOMEM, "plan needs %zu device bytes", L.total);
+    memset(plan, 0, sizeof(*plan));
+    plan->n = n; plan->lg_n = L.lg_n;
+    plan->fft_type = fft_type; plan->dtype = dtype;
+    plan->lg_n1 = L.lg_n1; plan->lg_n2 = L.lg_n2;
+    plan->four_shift = L.four_shift; plan->real_shift = L.real_shift;
+    plan->dev_base = dev_mem; plan->dev_bytes = L.total;
+    return dtype == DSC_CUDA_F64 ? build_tables<double>(plan, L, stream) : build_tables<float>(plan, L, stream);
+}
+
+size_t dsc_cuda_work_bytes(const dsc_cuda_plan *plan, int64_t lines) {
+    if (!plan_ok(plan) || plan->lg_n2 == 0 || lines <= 0) return 0;
+    const size_t es = plan->dtype == DSC_CUDA_F64 ? sizeof(double2) : sizeof(float2);
+    const size_t per_line = (size_t)plan->n * es * (plan->fft_type == DSC_CUDA_FFT_REAL ? 2 : 1);
+    return per_line * (size_t)lines;
+}
+
+int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *out,
+                 int64_t outer, int x_n, int64_t inner, int forward,
+                 void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || !x || !out || x_n < 1 || outer < 0 || inner < 1) return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft: bad argument");
+    const bool x_real = x_dtype == DSC_CUDA_F32 || x_dtype == DSC_CUDA_F64;
+    const int x_prec = (x_dtype == DSC_CUDA_F32 || x_dtype == DSC_CUDA_C32) ? DSC_CUDA_F32 : DSC_CUDA_F64;
+    if (x_prec != plan->dtype) return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft: input precision does not match the plan");
+    if (plan->dtype == DSC_CUDA_F32)
+        return forward ? run_fft<float, true>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream)
+                       : run_fft<float, false>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream);
+    return forward ? run_fft<double, true>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream)
+                   : run_fft<double, false>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream);
+}
+
+int dsc_cuda_rfft(const dsc_cuda_plan *plan, const void *x, void *out,
+                  int64_t outer, int x_n, int64_t inner, void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || plan->fft_type != DSC_CUDA_FFT_REAL || !x || !out || x_n < 1 || outer < 0 || inner < 1)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_rfft: bad argument");
+    return plan->dtype == DSC_CUDA_F32 ? run_rfft<float>(plan, x, out, outer, x_n, inner, work, work_bytes, stream)
+                                       : run_rfft<double>(plan, x, out, outer, x_n, inner, work, work_bytes, stream);
+}
+
+int dsc_cuda_irfft(const dsc_cuda_plan *plan, const void *x, void *out,
+                   int64_t outer, int x_n, int64_t inner, void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || plan->fft_type != DSC_CUDA_FFT_REAL || !x || !out || x_n < 1 || outer < 0 || inner < 1)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_irfft: bad argument");
+    return plan->dtype == DSC_CUDA_F32 ? run_irfft<float>(plan, x, out, outer, x_n, inner, work, work_bytes, stream)
+                                       : run_irfft<double>(plan, x, out, outer, x_n, inner, work, work_bytes, stream);
+}
+
+int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
+                  int64_t rows, int64_t cols, int b_rows, void *stream) {
+    if (!a || !b || !out || rows < 0 || cols < 0) return fail(DSC_CUDA_EINVAL, "dsc_cuda_cmul: bad argument");
+    const long long total = rows * cols;
+    if (total == 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (dtype == DSC_CUDA_C32)
+        DSC_LAUNCH(cmul_rows<float>, blocks, 256, 0, stream, (const float2 *)a, (const float2 *)b, (float2 *)out,
+                   (long long)rows, (long long)cols, b_rows);
+    else if (dtype == DSC_CUDA_C64)
+        DSC_LAUNCH(cmul_rows<double>, blocks, 256, 0, stream, (const double2 *)a, (const double2 *)b, (double2 *)out,
+                   (long long)rows, (long long)cols, b_rows);
+    else return fail(DSC_CUDA_EINVAL, "dsc_cuda_cmul: dtype %d is not complex", dtype);
+    return check_launch("cmul_rows");
+}
+
+}  // extern "C"

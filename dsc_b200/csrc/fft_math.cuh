@@ -1,0 +1,144 @@
+// fft_math.cuh -- register-resident complex arithmetic and radix-2/4/8/16 butterflies.
+//
+// Everything here works on values a thread already holds in registers; all array
+// indices are compile-time constants after unrolling, so nothing spills to local
+// memory.  Forward means e^{-i..} (the reference's sign = +1 branch,
+// /root/reference/dsc/include/dsc_fft.h:57-103,162); inverse is the conjugate.
+//
+// The file is plain CUDA C++ with no intrinsics so that tests/emul can compile
+// the very same code for the host and run thread blocks on pthreads.
+#pragma once
+
+#if defined(DSC_EMUL)
+#include "cuda_shim.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace dscfft {
+
+#define DSC_DEV __device__ __forceinline__
+
+// dynamic shared memory of the running block
+#if defined(DSC_EMUL)
+#define DSC_DYN_SMEM(name) unsigned char *name = dsc_emul::tls.smem
+#else
+#define DSC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+template <typename T> struct vec2;
+template <> struct vec2<float>  { using type = float2; };
+template <> struct vec2<double> { using type = double2; };
+template <typename T> using cx = typename vec2<T>::type;
+
+template <typename T> DSC_DEV cx<T> mk(T re, T im) { cx<T> r; r.x = re; r.y = im; return r; }
+template <typename V> DSC_DEV V cadd(V a, V b) { a.x += b.x; a.y += b.y; return a; }
+template <typename V> DSC_DEV V csub(V a, V b) { a.x -= b.x; a.y -= b.y; return a; }
+
+// a * w (FWD) or a * conj(w) (inverse); w is always a FORWARD twiddle e^{-i th}.
+template <bool FWD, typename V> DSC_DEV V cmul_tw(V a, V w) {
+    V r;
+    if (FWD) { r.x = a.x * w.x - a.y * w.y; r.y = a.x * w.y + a.y * w.x; }
+    else     { r.x = a.x * w.x + a.y * w.y; r.y = a.y * w.x - a.x * w.y; }
+    return r;
+}
+template <typename V> DSC_DEV V cmul(V a, V b) {
+    V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+
+// a * (-i) forward, a * (+i) inverse
+template <bool FWD, typename V> DSC_DEV V rot90(V a) {
+    V r;
+    if (FWD) { r.x = a.y; r.y = -a.x; } else { r.x = -a.y; r.y = a.x; }
+    return r;
+}
+
+template <typename T> struct consts {
+    static constexpr T sqrt1_2 = (T)0.70710678118654752440;
+    static constexpr T cos_pi_8 = (T)0.92387953251128675613;
+    static constexpr T sin_pi_8 = (T)0.38268343236508977173;
+};
+
+// a * w8^q, w8 = e^{-+ i pi/4}
+template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w8(cx<T> a) {
+    constexpr T h = consts<T>::sqrt1_2;
+    if (Q == 0) return a;
+    if (Q == 2) return rot90<FWD>(a);
+    if (Q == 1) return FWD ? mk<T>((a.x + a.y) * h, (a.y - a.x) * h)
+                           : mk<T>((a.x - a.y) * h, (a.x + a.y) * h);
+    /* Q == 3 */ return FWD ? mk<T>((a.y - a.x) * h, -(a.x + a.y) * h)
+                            : mk<T>(-(a.x + a.y) * h, (a.x - a.y) * h);
+}
+
+// a * w16^q for q in 0..9 (all the 4x4 decomposition needs), w16 = e^{-+ i pi/8}
+template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w16(cx<T> a) {
+    constexpr T c1 = consts<T>::cos_pi_8, s1 = consts<T>::sin_pi_8;
+    if (Q % 2 == 0) return mul_w8<FWD, (Q / 2) % 4, T>(Q >= 8 ? mk<T>(-a.x, -a.y) : a);
+    // odd q: cos/sin of q*pi/8 from the pi/8 pair
+    constexpr T c = (Q == 1) ? c1 : (Q == 3) ? s1 : (Q == 5) ? -s1 : (Q == 7) ? -c1 : /*9*/ -c1;
+    constexpr T s = (Q == 1) ? s1 : (Q == 3) ? c1 : (Q == 5) ? c1 : (Q == 7) ? s1 : /*9*/ -s1;
+    return FWD ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s)
+               : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
+}
+
+template <typename V> DSC_DEV void bfly2(V &a, V &b) {
+    const V t = a; a = cadd(t, b); b = csub(t, b);
+}
+
+// in-place DFT-4, natural order in and out
+template <bool FWD, typename V> DSC_DEV void bfly4(V &x0, V &x1, V &x2, V &x3) {
+    const V t0 = cadd(x0, x2), t1 = csub(x0, x2);
+    const V t2 = cadd(x1, x3), t3 = rot90<FWD>(csub(x1, x3));
+    x0 = cadd(t0, t2); x2 = csub(t0, t2);
+    x1 = cadd(t1, t3); x3 = csub(t1, t3);
+}
+
+// DFT-R of v[0..R), natural order in and out.  R in {2,4,8,16}.
+template <int R, bool FWD, typename T> struct Dft;
+
+template <bool FWD, typename T> struct Dft<1, FWD, T> {
+    static DSC_DEV void run(cx<T> (&)[1]) {}
+};
+template <bool FWD, typename T> struct Dft<2, FWD, T> {
+    static DSC_DEV void run(cx<T> (&v)[2]) { bfly2(v[0], v[1]); }
+};
+template <bool FWD, typename T> struct Dft<4, FWD, T> {
+    static DSC_DEV void run(cx<T> (&v)[4]) { bfly4<FWD>(v[0], v[1], v[2], v[3]); }
+};
+template <bool FWD, typename T> struct Dft<8, FWD, T> {
+    // m = 2a + b: two DFT-4 over a, twiddle w8^{b p1}, four DFT-2 over b
+    static DSC_DEV void run(cx<T> (&v)[8]) {
+        bfly4<FWD>(v[0], v[2], v[4], v[6]);
+        bfly4<FWD>(v[1], v[3], v[5], v[7]);
+        v[3] = mul_w8<FWD, 1, T>(v[3]);
+        v[5] = mul_w8<FWD, 2, T>(v[5]);
+        v[7] = mul_w8<FWD, 3, T>(v[7]);
+        bfly2(v[0], v[1]); bfly2(v[2], v[3]); bfly2(v[4], v[5]); bfly2(v[6], v[7]);
+        // v[2 p1 + p2] holds X[p1 + 4 p2]  ->  natural order
+        const cx<T> x1 = v[2], x2 = v[4], x3 = v[6], x4 = v[1], x5 = v[3], x6 = v[5];
+        v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6;
+    }
+};
+template <bool FWD, typename T> struct Dft<16, FWD, T> {
+    // m = 4a + b: four DFT-4 over a, twiddle w16^{b p1}, four DFT-4 over b
+    static DSC_DEV void run(cx<T> (&v)[16]) {
+        bfly4<FWD>(v[0], v[4], v[8], v[12]);
+        bfly4<FWD>(v[1], v[5], v[9], v[13]);
+        bfly4<FWD>(v[2], v[6], v[10], v[14]);
+        bfly4<FWD>(v[3], v[7], v[11], v[15]);
+        // v[b + 4 p1] = y_b[p1]
+        v[5]  = mul_w16<FWD, 1, T>(v[5]);  v[6]  = mul_w16<FWD, 2, T>(v[6]);  v[7]  = mul_w16<FWD, 3, T>(v[7]);
+        v[9]  = mul_w16<FWD, 2, T>(v[9]);  v[10] = mul_w16<FWD, 4, T>(v[10]); v[11] = mul_w16<FWD, 6, T>(v[11]);
+        v[13] = mul_w16<FWD, 3, T>(v[13]); v[14] = mul_w16<FWD, 6, T>(v[14]); v[15] = mul_w16<FWD, 9, T>(v[15]);
+        bfly4<FWD>(v[0], v[1], v[2], v[3]);
+        bfly4<FWD>(v[4], v[5], v[6], v[7]);
+        bfly4<FWD>(v[8], v[9], v[10], v[11]);
+        bfly4<FWD>(v[12], v[13], v[14], v[15]);
+        // v[4 p1 + p2] holds X[p1 + 4 p2]: transpose the 4x4 register tile
+#define DSC_SWAP(i, j) { const cx<T> s_ = v[i]; v[i] = v[j]; v[j] = s_; }
+        DSC_SWAP(1, 4) DSC_SWAP(2, 8) DSC_SWAP(3, 12) DSC_SWAP(6, 9) DSC_SWAP(7, 13) DSC_SWAP(11, 14)
+#undef DSC_SWAP
+    }
+};
+
+}  // namespace dscfft

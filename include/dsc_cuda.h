@@ -1,0 +1,103 @@
+/* dsc_cuda.h -- the thin extern "C" layer between DSC's host C++ and the sm_100a kernels.
+ *
+ * This is the only header where device pointers and streams appear; dsc.h stays CUDA-free.
+ * Everything is plain C: raw pointers, 64-bit counts, `void *stream` (a cudaStream_t).
+ * No function here allocates device memory: plans and work buffers are carved by the caller
+ * from the device arena that dsc_ctx_init reserves once (dsc_arena.cpp).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   dsc_cuda_plan_bytes  <- dsc_fft_storage             dsc/include/dsc_fft.h:109-135
+ *   dsc_cuda_plan_build  <- dsc_init_plan               dsc/include/dsc_fft.h:33-55,137-154
+ *   dsc_cuda_fft         <- exec_fft + dsc_complex_fft  dsc/src/dsc.cpp:1958-2007, dsc_fft.h:156-176
+ *   dsc_cuda_rfft/irfft  <- exec_rfft + dsc_real_fft    dsc/src/dsc.cpp:2102-2171, dsc_fft.h:178-238
+ *   dsc_cuda_cmul        <- binary_op<mul_op> (complex) dsc/src/dsc.cpp:1186-1245, dsc_ops.h:68-78
+ *   dsc_cuda_filter      <- README filterFFT            README.md:118-134 (rfft, *, irfft fused)
+ *
+ * Every entry point returns 0 on success or a negative DSC_CUDA_E* code; the message of
+ * the last failure is available from dsc_cuda_last_error().  Launches are asynchronous on
+ * `stream`; the caller synchronises.
+ */
+#ifndef DSC_CUDA_H
+#define DSC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same numeric values as dsc_dtype (dsc_dtype.h:51-56) and dsc_fft_type (dsc_fft.h:13-16) */
+enum { DSC_CUDA_F32 = 0, DSC_CUDA_F64 = 1, DSC_CUDA_C32 = 2, DSC_CUDA_C64 = 3 };
+enum { DSC_CUDA_FFT_REAL = 0, DSC_CUDA_FFT_COMPLEX = 1 };
+
+enum {
+    DSC_CUDA_OK = 0,
+    DSC_CUDA_EINVAL = -1,     /* bad argument (dtype, length, null pointer) */
+    DSC_CUDA_ENOMEM = -2,     /* caller-provided plan / work memory too small */
+    DSC_CUDA_ELAUNCH = -3,    /* CUDA runtime error, see dsc_cuda_last_error() */
+    DSC_CUDA_EUNSUPPORTED = -4
+};
+
+#define DSC_CUDA_MAX_STAGES 5
+
+/* A plan = the radix schedule for a power-of-two length plus its twiddle tables in HBM.
+ * `n` is the COMPLEX transform length; a REAL plan of order n serves 2n-sample real
+ * transforms and carries one more table (W_2n^k), like the reference's REAL plans. */
+typedef struct dsc_cuda_plan {
+    int n, lg_n;
+    int fft_type;               /* DSC_CUDA_FFT_REAL | DSC_CUDA_FFT_COMPLEX */
+    int dtype;                  /* DSC_CUDA_F32 | DSC_CUDA_F64: precision of the tables */
+    int lg_n1, lg_n2;           /* n = n1 * n2; lg_n2 == 0: single shared-memory pass */
+    int four_shift;             /* split point of the inter-pass twiddle index */
+    void *dev_base;             /* block handed to dsc_cuda_plan_build */
+    size_t dev_bytes;
+    void *tw1[DSC_CUDA_MAX_STAGES];   /* stage tables of the length-n1 transform */
+    void *tw2[DSC_CUDA_MAX_STAGES];   /* stage tables of the length-n2 transform */
+    void *tw_lo, *tw_hi;        /* W_n^p split tables for the inter-pass twiddle */
+    void *tw_real;              /* REAL plans, single pass: W_2n^k, k <= n/2 */
+    void *tw_real_lo, *tw_real_hi;  /* REAL plans, two-pass: W_2n^p split the same way */
+    int real_shift;
+} dsc_cuda_plan;
+
+const char *dsc_cuda_last_error(void);
+int dsc_cuda_device_count(void);
+
+/* Device bytes a plan for (n, type, dtype) needs.  n must be a power of two >= 1. */
+size_t dsc_cuda_plan_bytes(int n, int fft_type, int dtype);
+
+/* Fill `plan` and compute its tables into dev_mem (>= dsc_cuda_plan_bytes, 256-B aligned). */
+int dsc_cuda_plan_build(dsc_cuda_plan *plan, int n, int fft_type, int dtype,
+                        void *dev_mem, size_t dev_bytes, void *stream);
+
+/* Work bytes needed to transform `lines` lines with this plan (0 for single-pass plans).
+ * Any smaller non-zero amount that holds at least one line also works: the launch is
+ * chunked.  Two-pass plans keep their intermediate here so it can stay L2-resident. */
+size_t dsc_cuda_work_bytes(const dsc_cuda_plan *plan, int64_t lines);
+
+/* fft / ifft along the middle axis of a contiguous (outer, x_n, inner) tensor.
+ * x_dtype in {F32,F64,C32,C64}; out is complex of the plan's precision with extent plan->n
+ * along the axis.  min(x_n, n) elements are read per line, the rest is zero (pad / crop). */
+int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *out,
+                 int64_t outer, int x_n, int64_t inner, int forward,
+                 void *work, size_t work_bytes, void *stream);
+
+/* rfft: real (outer, x_n, inner) -> complex (outer, n + 1, inner), plan REAL of order n. */
+int dsc_cuda_rfft(const dsc_cuda_plan *plan, const void *x, void *out,
+                  int64_t outer, int x_n, int64_t inner,
+                  void *work, size_t work_bytes, void *stream);
+
+/* irfft: complex (outer, x_n, inner) bins -> real (outer, 2n, inner); min(x_n, n+1) bins read. */
+int dsc_cuda_irfft(const dsc_cuda_plan *plan, const void *x, void *out,
+                   int64_t outer, int x_n, int64_t inner,
+                   void *work, size_t work_bytes, void *stream);
+
+/* out = a * b elementwise on complex rows; b has `cols` elements (b_rows == 0, broadcast)
+ * or rows*cols (b_rows != 0). */
+int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
+                  int64_t rows, int64_t cols, int b_rows, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,164 @@
+"""numpy-facing driver of the device-level C ABI (dsc_cuda_*), for tests.
+
+backend='numpy': "device" memory is host memory -- used with tests/emul/libdsc_emul.so,
+                 the pthread emulation of the kernels (no GPU needed).
+backend='torch': device memory comes from torch CUDA tensors -- used with the real
+                 dsc_b200/libdsc.so on a B200.
+Shape rules are taken from the oracle so that only the kernels are under test here.
+"""
+import numpy as np
+
+from dsc_b200 import cuda_api
+from oracle import port
+
+_CODE = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2, np.dtype(np.complex128): 3}
+_CPLX = {np.dtype(np.float32): np.complex64, np.dtype(np.float64): np.complex128,
+         np.dtype(np.complex64): np.complex64, np.dtype(np.complex128): np.complex128}
+_REAL = {np.dtype(np.complex64): np.float32, np.dtype(np.complex128): np.float64}
+
+
+class _NumpyMem:
+    def alloc(self, nbytes):
+        buf = np.zeros(max(nbytes, 256) + 256, dtype=np.uint8)
+        off = (-buf.ctypes.data) % 256
+        return buf[off:off + max(nbytes, 256)]
+
+    def ptr(self, buf):
+        return buf.ctypes.data
+
+    def upload(self, a):
+        return np.ascontiguousarray(a).copy()
+
+    def empty(self, shape, dtype, fill=None):
+        out = np.empty(shape, dtype=dtype)
+        out.view(np.uint8).reshape(-1)[:] = 0xCD       # poison: unwritten output shows up
+        return out
+
+    def download(self, buf):
+        return buf
+
+    def sync(self):
+        pass
+
+
+class _TorchMem:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda:0")
+
+    def alloc(self, nbytes):
+        return self.torch.zeros(max(nbytes, 256), dtype=self.torch.uint8, device=self.dev)
+
+    def ptr(self, buf):
+        return buf.data_ptr()
+
+    def upload(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+
+    def empty(self, shape, dtype, fill=None):
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        t = self.torch.full((max(nbytes, 1),), 0xCD, dtype=self.torch.uint8, device=self.dev)
+        t._np_shape, t._np_dtype = tuple(shape), np.dtype(dtype)
+        return t
+
+    def download(self, buf):
+        self.torch.cuda.synchronize()
+        host = buf.cpu().numpy()
+        if hasattr(buf, "_np_shape"):
+            n = int(np.prod(buf._np_shape, dtype=np.int64)) * buf._np_dtype.itemsize
+            return host[:n].view(buf._np_dtype).reshape(buf._np_shape)
+        return host
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+
+class DevFFT:
+    def __init__(self, lib_path, backend="numpy", work_lines=None):
+        self.api = cuda_api.CudaApi(lib_path)
+        self.mem = _NumpyMem() if backend == "numpy" else _TorchMem()
+        self.plans = {}
+        self.work_lines = work_lines      # None: full-size work buffer; k: force chunking by k lines
+
+    def plan(self, n, fft_type, prec):
+        key = (n, fft_type, prec)
+        if key not in self.plans:
+            nbytes = self.api.plan_bytes(n, fft_type, prec)
+            assert nbytes > 0, f"plan_bytes({n}) == 0"
+            block = self.mem.alloc(nbytes)
+            p = self.api.plan_build(n, fft_type, prec, self.mem.ptr(block), nbytes)
+            self.mem.sync()
+            self.plans[key] = (p, block)
+        return self.plans[key][0]
+
+    def _work(self, plan, lines):
+        nbytes = self.api.work_bytes(plan, lines if self.work_lines is None else min(lines, self.work_lines))
+        if nbytes == 0:
+            return None, 0, 0
+        w = self.mem.alloc(nbytes)
+        return w, self.mem.ptr(w), nbytes
+
+    @staticmethod
+    def _split(x, axis):
+        ax = (4 + axis if axis < 0 else 4 - x.ndim + axis) - (4 - x.ndim)   # dsc.h:81
+        assert 0 <= ax < x.ndim
+        outer = int(np.prod(x.shape[:ax], dtype=np.int64))
+        inner = int(np.prod(x.shape[ax + 1:], dtype=np.int64))
+        return ax, outer, x.shape[ax], inner
+
+    def _cfft(self, x, n, axis, forward):
+        x = np.ascontiguousarray(x)
+        ax, outer, x_n, inner = self._split(x, axis)
+        fft_n = port.fft_len(x_n, n)
+        prec = 0 if x.dtype in (np.float32, np.complex64) else 1
+        plan = self.plan(fft_n, cuda_api.FFT_COMPLEX, prec)
+        shape = list(x.shape); shape[ax] = fft_n
+        dx = self.mem.upload(x)
+        dout = self.mem.empty(shape, _CPLX[x.dtype])
+        w, wp, wb = self._work(plan, outer * inner)
+        self.api.fft(plan, self.mem.ptr(dx), _CODE[x.dtype], self.mem.ptr(dout), outer, x_n, inner, forward, wp, wb)
+        return self.mem.download(dout)
+
+    def fft(self, x, n=-1, axis=-1):
+        return self._cfft(x, n, axis, True)
+
+    def ifft(self, x, n=-1, axis=-1):
+        return self._cfft(x, n, axis, False)
+
+    def rfft(self, x, n=-1, axis=-1):
+        x = np.ascontiguousarray(x)
+        ax, outer, x_n, inner = self._split(x, axis)
+        order, out_n = port.rfft_len(x_n, n)
+        prec = 0 if x.dtype == np.float32 else 1
+        plan = self.plan(order, cuda_api.FFT_REAL, prec)
+        shape = list(x.shape); shape[ax] = out_n
+        dx = self.mem.upload(x)
+        dout = self.mem.empty(shape, _CPLX[x.dtype])
+        w, wp, wb = self._work(plan, outer * inner)
+        self.api.rfft(plan, self.mem.ptr(dx), self.mem.ptr(dout), outer, x_n, inner, wp, wb)
+        return self.mem.download(dout)
+
+    def irfft(self, x, n=-1, axis=-1):
+        x = np.ascontiguousarray(x)
+        ax, outer, x_n, inner = self._split(x, axis)
+        order, out_n = port.irfft_len(x_n, n)
+        prec = 0 if x.dtype == np.complex64 else 1
+        plan = self.plan(order, cuda_api.FFT_REAL, prec)
+        shape = list(x.shape); shape[ax] = out_n
+        dx = self.mem.upload(x)
+        dout = self.mem.empty(shape, _REAL[x.dtype])
+        w, wp, wb = self._work(plan, outer * inner)
+        self.api.irfft(plan, self.mem.ptr(dx), self.mem.ptr(dout), outer, x_n, inner, wp, wb)
+        return self.mem.download(dout)
+
+    def cmul(self, a, b):
+        a = np.ascontiguousarray(a)
+        b = np.ascontiguousarray(b, dtype=a.dtype)
+        rows = int(np.prod(a.shape[:-1], dtype=np.int64))
+        cols = a.shape[-1]
+        da, db = self.mem.upload(a), self.mem.upload(b)
+        dout = self.mem.empty(a.shape, a.dtype)
+        self.api.cmul(self.mem.ptr(da), self.mem.ptr(db), self.mem.ptr(dout), _CODE[a.dtype], rows, cols,
+                      b.size == a.size and rows > 1)
+        return self.mem.download(dout)

@@ -1,0 +1,185 @@
+"""Functional check of the CUDA sources WITHOUT a GPU.
+
+tests/emul compiles dsc_b200/csrc/*.cu with g++ against a pthread shim of the CUDA
+execution model (blocks, threads, __syncthreads, dynamic shared memory), so the index
+arithmetic of every kernel -- Stockham scatter and padding, pad/crop predicates, strided
+thread mapping, real un-mixing, four-step geometry and chunking -- is exercised here against
+the oracle.  This is test infrastructure; the real parity tests are tests/test_gpu_*.py.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import port
+from tests.devfft import DevFFT
+from tests.util import TOL, randn, rel_l2
+
+EMUL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+# the reference itself is ~3e-7 / 9e-16 away from exact; leave the rest of the budget unused
+TIGHT = {"complex64": 1e-6, "float32": 1e-6, "complex128": 4e-15, "float64": 4e-15}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    subprocess.run(["make", "-s", "-j8", "-C", EMUL_DIR], check=True)
+    return DevFFT(os.path.join(EMUL_DIR, "libdsc_emul.so"))
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("lg", list(range(0, 15)))
+def test_c2c_last_axis(dev, dtype, lg):
+    if dtype == "complex128" and lg > 13:
+        pytest.skip("two-pass for complex128")
+    rng = np.random.default_rng(lg)
+    rows = 3 if lg < 12 else 1
+    x = randn(rng, (rows, 1 << lg), dtype)
+    y = dev.fft(x)
+    assert y.shape == x.shape and y.dtype == x.dtype
+    assert rel_l2(y, port.fft(x)) < TIGHT[dtype]
+    z = dev.ifft(y)
+    assert rel_l2(z, port.ifft(y)) < TIGHT[dtype]
+    assert rel_l2(z, x) < TIGHT[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "complex64", "complex128"])
+def test_all_axes_pad_crop(dev, dtype):
+    # python/tests/test_ops.py:458-489: every axis of a 4-D tensor, n in {crop, copy, pad}
+    rng = np.random.default_rng(5)
+    for axis in range(4):
+        shape = [3, 4, 2, 5]
+        shape[axis] = 16
+        x = randn(rng, shape, dtype)
+        for n in (8, 16, 32, -1):
+            for ax in (axis, axis - 4):
+                y = dev.fft(x, n, ax)
+                want = port.fft(x, n, ax)
+                assert y.shape == want.shape and y.dtype == want.dtype
+                assert rel_l2(y, want) < TIGHT[dtype]
+            yi = dev.ifft(x, n, axis)
+            assert rel_l2(yi, port.ifft(x, n, axis)) < TIGHT[dtype]
+
+
+def test_non_pow2_lengths(dev):
+    rng = np.random.default_rng(6)
+    x = randn(rng, (7, 10), "float32")
+    assert dev.fft(x).shape == (7, 16)
+    assert rel_l2(dev.fft(x), port.fft(x)) < 1e-6
+    assert rel_l2(dev.fft(x, 5), port.fft(x, 5)) < 1e-6          # n=5 -> 8, crop to 8
+    assert rel_l2(dev.fft(x, axis=0), port.fft(x, axis=0)) < 1e-6  # 7 -> 8 along axis 0
+    x = randn(rng, (100, 3), "complex128")
+    assert rel_l2(dev.ifft(x, axis=0), port.ifft(x, axis=0)) < 4e-15
+
+
+def test_many_lines_partial_blocks(dev):
+    rng = np.random.default_rng(8)
+    for shape in [(37, 64), (301, 16), (5, 512), (1000, 4), (19, 2), (33, 1)]:
+        x = randn(rng, shape, "complex64")
+        assert rel_l2(dev.fft(x), port.fft(x)) < 1e-6
+    x = randn(rng, (64, 37), "complex64")        # strided, 37 lines
+    assert rel_l2(dev.fft(x, axis=0), port.fft(x, axis=0)) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("lg", list(range(0, 14)))
+def test_rfft_irfft_last_axis(dev, dtype, lg):
+    # order 2^lg <-> 2^(lg+1) real samples
+    rng = np.random.default_rng(100 + lg)
+    rows = 3 if lg < 12 else 1
+    x = randn(rng, (rows, 2 << lg), dtype)
+    y = dev.rfft(x)
+    want = port.rfft(x)
+    assert y.shape == want.shape and y.dtype == want.dtype
+    assert rel_l2(y, want) < TIGHT[dtype]
+    assert np.all(y[:, 0].imag == 0) and np.all(y[:, -1].imag == 0)   # dsc_fft.h:220-225
+    z = dev.irfft(want)
+    wz = port.irfft(want)
+    assert z.shape == wz.shape and z.dtype == wz.dtype
+    assert rel_l2(z, wz) < TIGHT[dtype]
+    assert rel_l2(z, x) < TIGHT[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_rfft_axes_and_length_rules(dev, dtype):
+    rng = np.random.default_rng(9)
+    cdt = np.complex64 if dtype == "float32" else np.complex128
+    for axis in range(3):
+        shape = [3, 4, 5]
+        shape[axis] = 32
+        x = randn(rng, shape, dtype)
+        for n in (-1, 16, 64, 10):
+            y = dev.rfft(x, n, axis)
+            want = port.rfft(x, n, axis)
+            assert y.shape == want.shape
+            assert rel_l2(y, want) < TIGHT[dtype]
+            for nb in (-1, 3, want.shape[axis] + 3):       # irfft n counts input bins
+                z = dev.irfft(want, nb, axis)
+                wz = port.irfft(want, nb, axis)
+                assert z.shape == wz.shape
+                assert rel_l2(z, wz) < TIGHT[dtype]
+    # DC / Nyquist imaginary parts of the input are ignored by irfft (dsc_fft.h:227-228)
+    X = randn(rng, (2, 17), cdt)
+    assert rel_l2(dev.irfft(X), port.irfft(X)) < TIGHT[dtype]
+    # Appendix A
+    x = randn(rng, (10,), dtype)
+    assert dev.rfft(x).shape == (9,) and dev.rfft(x, 4).shape == (3,)
+    X = port.rfft(x)
+    assert dev.irfft(X).shape == (16,) and dev.irfft(X, 16).shape == (32,) and dev.irfft(X, 5).shape == (8,)
+    x2 = randn(rng, (2,), dtype)
+    assert rel_l2(dev.rfft(x2), port.rfft(x2)) < TIGHT[dtype]
+    assert rel_l2(dev.irfft(port.rfft(x2)), port.irfft(port.rfft(x2))) < TIGHT[dtype]
+
+
+@pytest.mark.parametrize("dtype,lg", [("complex64", 15), ("complex64", 17), ("complex128", 14), ("complex128", 16)])
+def test_two_pass_c2c(dev, dtype, lg):
+    rng = np.random.default_rng(lg)
+    x = randn(rng, (2, 1 << lg), dtype)
+    y = dev.fft(x)
+    assert rel_l2(y, port.fft(x)) < TIGHT[dtype]
+    z = dev.ifft(y)
+    assert rel_l2(z, x) < TIGHT[dtype]
+    # pad and crop through the first pass predicate; real input cast
+    xs = x[:, : (1 << lg) - 1000]
+    assert rel_l2(dev.fft(xs), port.fft(xs)) < TIGHT[dtype]
+    xr = xs.real.copy()
+    assert rel_l2(dev.fft(xr), port.fft(xr)) < TIGHT[dtype]
+
+
+def test_two_pass_chunked_work_buffer():
+    d = DevFFT(os.path.join(EMUL_DIR, "libdsc_emul.so"), work_lines=2)
+    rng = np.random.default_rng(3)
+    x = randn(rng, (5, 1 << 15), "complex64")
+    assert rel_l2(d.fft(x), port.fft(x)) < 1e-6
+    xr = randn(rng, (3, 1 << 16), "float32")
+    d1 = DevFFT(os.path.join(EMUL_DIR, "libdsc_emul.so"), work_lines=1)
+    X = d1.rfft(xr)
+    assert rel_l2(X, port.rfft(xr)) < 1e-6
+    assert rel_l2(d1.irfft(X), xr) < 1e-6
+
+
+@pytest.mark.parametrize("dtype,lg", [("float32", 15), ("float64", 14)])
+def test_two_pass_real(dev, dtype, lg):
+    rng = np.random.default_rng(lg)
+    x = randn(rng, (2, 2 << lg), dtype)
+    y = dev.rfft(x)
+    want = port.rfft(x)
+    assert y.shape == want.shape
+    assert rel_l2(y, want) < TIGHT[dtype]
+    assert np.all(y[:, 0].imag == 0) and np.all(y[:, -1].imag == 0)
+    z = dev.irfft(want)
+    assert rel_l2(z, port.irfft(want)) < TIGHT[dtype]
+    xs = x[:, :-777]                                   # zero-padded real input
+    assert rel_l2(dev.rfft(xs, n=2 << lg), port.rfft(xs, n=2 << lg)) < TIGHT[dtype]
+    Xs = want[:, :-5]                                  # fewer bins than order+1
+    assert rel_l2(dev.irfft(Xs, n=want.shape[1]), port.irfft(Xs, n=want.shape[1])) < TIGHT[dtype]
+
+
+def test_cmul(dev):
+    rng = np.random.default_rng(1)
+    for dt in ("complex64", "complex128"):
+        a = randn(rng, (5, 129), dt)
+        b = randn(rng, (129,), dt)
+        assert rel_l2(dev.cmul(a, b), a * b) < TOL[np.dtype(dt)] / 10
+        b2 = randn(rng, (5, 129), dt)
+        assert rel_l2(dev.cmul(a, b2), a * b2) < TOL[np.dtype(dt)] / 10
