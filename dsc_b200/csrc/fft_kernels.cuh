@@ -389,7 +389,7 @@ __global__ void fill_power_twiddles(cx<T> *out, long long count, long long mult,
 // Frequency-domain pointwise product (mul_op, /root/reference/dsc/include/dsc_ops.h:68-78),
 // b broadcast over rows when b_rows == 0.
 template <typename T>
-__global__ void cmul_rows(const cx<T> *__restrict__ a, const cx<T> *__restrict__ b, cx<T> *__restrict__ out,
+__global__ void cmul_rows(const cx<T> *a, const cx<T> *__restrict__ b, cx<T> *out,   // out may alias a
                           long long rows, long long cols, int b_rows) {
     const long long total = rows * cols;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;

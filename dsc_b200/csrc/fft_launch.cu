@@ -39,9 +39,6 @@ inline int check_launch(const char *what) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
 
-template <typename T> constexpr int dtype_of();
-template <> constexpr int dtype_of<float>() { return DSC_CUDA_F32; }
-template <> constexpr int dtype_of<double>() { return DSC_CUDA_F64; }
 
 // ---- plan geometry -------------------------------------------------------------------
 

@@ -1,0 +1,182 @@
+"""Parity cases for the tensor-level C ABI (dsc_fft / dsc_ifft / dsc_rfft / dsc_irfft, plan cache,
+tracer, residency), shared by the emulated (CPU) and the real (B200) runs.  Each function takes
+the bound `dsc_b200` module; the oracle is the C restatement in oracle/ (pinned bit-exact to the
+reference) and the golden vectors recorded from the reference itself."""
+import json
+import os
+import tempfile
+
+import numpy as np
+
+from oracle import port
+from tests.util import TOL, load_golden, randn, rel_l2
+
+
+def check_golden(dsc):
+    n = 0
+    for i, m, a in load_golden():
+        op = m["op"]
+        if op in ("fft", "ifft", "rfft", "irfft"):
+            got = getattr(dsc, op)(a["x"], n=m["n"], axis=m["axis"]).numpy()
+        elif op == "mul":
+            got = dsc.mul(a["x"], a["b"]).numpy()
+        elif op == "filter":
+            S = dsc.rfft(a["x"], n=m["n"])
+            B = dsc.rfft(a["b"], n=m["n"])
+            got = dsc.irfft(S * B).numpy()
+        else:
+            continue
+        want = a["y"]
+        assert got.shape == want.shape and got.dtype == want.dtype, (i, m, got.shape, want.shape)
+        assert rel_l2(got, want) < TOL[want.dtype], (i, m, rel_l2(got, want))
+        n += 1
+    assert n > 150
+
+
+def check_shapes_appendix_a(dsc):
+    rng = np.random.default_rng(11)
+    x = randn(rng, (10,), "float32")
+    y = dsc.fft(x)
+    assert y.shape == (16,) and y.dtype == np.complex64
+    assert rel_l2(y.numpy(), np.fft.fft(x.astype(np.float64), n=16)) < 1e-5
+    assert dsc.fft(x, n=5).shape == (8,)
+    assert rel_l2(dsc.fft(x, n=5).numpy(), np.fft.fft(x[:8].astype(np.float64))) < 1e-5
+    assert dsc.rfft(x).shape == (9,) and dsc.rfft(x, n=4).shape == (3,)
+    X = dsc.rfft(x)
+    assert dsc.irfft(X).shape == (16,) and dsc.irfft(X, n=9).shape == (16,)
+    assert dsc.irfft(X, n=16).shape == (32,) and dsc.irfft(X, n=5).shape == (8,)
+    assert rel_l2(dsc.irfft(X, n=16).numpy(), np.fft.irfft(X.numpy().astype(np.complex128), n=32)) < 1e-5
+    assert dsc.ifft(x).dtype == np.complex64                      # real input is cast, then inverted
+    x3 = randn(rng, (4, 8, 16), "float64")
+    for axis in range(-3, 3):
+        assert rel_l2(dsc.fft(x3, axis=axis).numpy(), np.fft.fft(x3, axis=axis)) < 1e-12
+
+
+def check_out_param(dsc):
+    rng = np.random.default_rng(12)
+    x = randn(rng, (6, 64), "complex64")
+    out = dsc.from_numpy(np.zeros((6, 64), np.complex64))
+    res = dsc.fft(x, out=out)
+    assert rel_l2(out.numpy(), port.fft(x)) < 1e-6
+    assert np.array_equal(res.numpy(), out.numpy())
+    xr = randn(rng, (3, 32), "float64")
+    out = dsc.from_numpy(np.zeros((3, 17), np.complex128))
+    dsc.rfft(xr, out=out)
+    assert rel_l2(out.numpy(), port.rfft(xr)) < 1e-14
+
+
+def check_vs_oracle_sweep(dsc, max_lg=12):
+    rng = np.random.default_rng(13)
+    for dtype in ("float32", "float64", "complex64", "complex128"):
+        for shape, n, axis in [((5, 128), -1, -1), ((16, 7), -1, 0), ((3, 4, 32, 2), 64, 2), ((2, 1 << max_lg), -1, 1),
+                               ((9, 33), 16, -1)]:
+            x = randn(rng, shape, dtype)
+            for op in ("fft", "ifft"):
+                got = getattr(dsc, op)(x, n=n, axis=axis).numpy()
+                want = getattr(port, op)(x, n, axis)
+                assert got.shape == want.shape and got.dtype == want.dtype
+                assert rel_l2(got, want) < TOL[want.dtype] / 5
+            if np.dtype(dtype).kind == "f":
+                X = dsc.rfft(x, n=n, axis=axis)
+                want = port.rfft(x, n, axis)
+                assert X.shape == want.shape
+                assert rel_l2(X.numpy(), want) < TOL[want.dtype] / 5
+                back = dsc.irfft(X, axis=axis).numpy()
+                wb = port.irfft(want, -1, axis)
+                assert back.shape == wb.shape and rel_l2(back, wb) < TOL[wb.dtype] / 5
+
+
+def check_filter_pipeline(dsc):
+    # BASELINE configs[0]: README filterFFT (README.md:118-134)
+    s = np.random.default_rng(0).standard_normal(8192).astype(np.float32)
+    b = np.random.default_rng(1).standard_normal(128).astype(np.float32)
+    want = port.filter_fft(s, b, 16384)
+    B = dsc.rfft(b, n=16384)
+    unfused = dsc.irfft(dsc.rfft(s, n=16384) * B)
+    assert rel_l2(unfused.numpy(), want) < 1e-5
+    fused = dsc.fft_filter(s, B, n=16384)
+    assert fused.shape == (16384,)
+    assert rel_l2(fused.numpy(), want) < 1e-5
+    conv = np.convolve(s.astype(np.float64), b.astype(np.float64))
+    assert rel_l2(fused[:8319].numpy(), conv) < 1e-5            # the README's [:output_length] crop
+    # batched channels, broadcast spectrum
+    S = randn(np.random.default_rng(2), (5, 1000), "float32")
+    Bs = dsc.rfft(b, n=2048)
+    got = dsc.fft_filter(S, Bs, n=2048).numpy()
+    for r in range(5):
+        assert rel_l2(got[r], port.filter_fft(S[r], b, 2048)) < 1e-5
+
+
+def check_plan_cache(dsc, max_lg=12):
+    # > DSC_MAX_FFT_PLANS distinct plans: results stay right, device usage plateaus (eviction frees)
+    rng = np.random.default_rng(14)
+    usage = []
+    for rnd in range(2):
+        for lg in range(1, max_lg + 1):
+            for dtype in ("complex64", "complex128"):
+                x = randn(rng, (2, 1 << lg), dtype)
+                assert rel_l2(dsc.fft(x).numpy(), port.fft(x)) < TOL[x.dtype] / 5
+        usage.append(dsc.device_used_mem())
+    assert 2 * max_lg > 16
+    assert usage[0] == usage[1], usage
+    assert dsc.device_alloc_calls() == 1, "the device arena is the only device allocation"
+
+
+def check_memory_accounting(dsc):
+    base_h, base_d = dsc.used_mem(), dsc.device_used_mem()
+    rng = np.random.default_rng(15)
+    for _ in range(3):
+        x = dsc.from_numpy(randn(rng, (8, 256), "complex64"))
+        y = dsc.fft(x)
+        z = dsc.ifft(y)
+        del x, y, z
+    assert dsc.used_mem() == base_h
+    assert dsc.device_used_mem() == base_d
+
+
+def check_residency_modes(dsc):
+    rng = np.random.default_rng(16)
+    x = randn(rng, (32, 512), "complex64")
+    want = port.ifft(port.fft(x))
+    try:
+        for mode in (1, 2):
+            dsc.set_residency(mode)
+            y = dsc.fft(x)
+            z = dsc.ifft(y)                   # y never re-uploaded; in mode 2 never downloaded either
+            assert rel_l2(z.numpy(), want) < 1e-6
+            assert rel_l2(y.numpy(), port.fft(x)) < 1e-6
+            prod = y * y                      # host op on a device-resident tensor syncs it first
+            assert rel_l2(prod.numpy(), port.fft(x) ** 2) < 1e-5
+            del y, z, prod
+    finally:
+        dsc.set_residency(0)
+
+
+def check_traces(dsc):
+    rng = np.random.default_rng(17)
+    x = dsc.from_numpy(randn(rng, (4, 64), "float32"))
+    dsc.clear_traces()
+    dsc.traces_record(True)
+    y = dsc.fft(x)
+    r = dsc.rfft(x)
+    dsc.traces_record(False)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "traces.json")
+        dsc.dump_traces(path)
+        events = json.load(open(path))
+    dsc.clear_traces()
+    names = [(e["name"], e["cat"], e["ph"]) for e in events]
+    # reference names / categories (dsc_tracing.h:20-21, 90, 94)
+    assert ("dsc_internal_fft", "op;fft", "B") in names and ("dsc_internal_fft", "op;fft", "E") in names
+    assert ("dsc_internal_rfft", "op;fft", "B") in names
+    assert ("dsc_plan_fft", "op;fft;plan", "B") in names
+    fft_b = next(e for e in events if e["name"] == "dsc_internal_fft" and e["ph"] == "B")
+    assert fft_b["args"]["type"] == "FFT" and fft_b["args"]["order"] == -1 and fft_b["args"]["axis"] == -1
+    assert fft_b["args"]["x"]["shape"] == "[4, 64]" and fft_b["args"]["x"]["dtype"] == "f32"
+    plan_b = next(e for e in events if e["name"] == "dsc_plan_fft" and e["ph"] == "B")
+    assert plan_b["args"] == {"type": "FFT", "n": 64, "order": 64, "dtype": "c32"}
+    # new: device spans as complete events with a duration
+    gpu = [e for e in events if e["cat"] == "gpu;fft"]
+    assert gpu and all(e["ph"] == "X" and e["dur"] >= 0 and e["args"]["n"] in (64, 32) for e in gpu)
+    assert any(e["cat"] == "gpu;copy" for e in events)
+    del y, r
