@@ -277,6 +277,14 @@ def run_ours(args, rank, world, local_rank):
     err = float(((z[:64] - x[:64]).norm() / x[:64].norm()).item())
 
     # ---- end-to-end leg: drop-in tensor C ABI with host buffers -------------------------------
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms_per_step, "note": "profiling run (--no-e2e): not a bench line",
+                              "roofline": {"achieved": achieved, "peak": peak, "frac": achieved / peak, "launch_ms": launch_ms}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     del y, z
     x_host = torch.view_as_real(x[: rows]).cpu().numpy().view(np.complex64).reshape(rows, N_POINTS)
     del x
@@ -342,6 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

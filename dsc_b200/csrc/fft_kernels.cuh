@@ -31,6 +31,8 @@ enum Mode : int {
     MODE_C2C = 0,   // complex / real-cast / real-pair / staged-row input -> complex out
     MODE_R2C = 1,   // rfft : 2N reals -> N+1 bins, un-mixing fused after the last stage
     MODE_C2R = 2,   // irfft: N+1 bins -> 2N reals, mixing fused before the first stage
+    MODE_FAST = 3,  // dense complex lines (inner == 1, no pad/crop, whole blocks): the bandwidth path --
+                    // one base pointer per thread, immediate offsets, streaming cache hints
 };
 
 // how MODE_C2C reads its input
@@ -79,6 +81,12 @@ template <int LG_N, int LG_E> struct Sched {
     // padded length of one line in shared memory (+1 keeps adjacent lines on different banks)
     static constexpr int LINE = N + (N >> LG_E) + 1;
     static DSC_DEV int pad(int i) { return i + (i >> LG_E); }
+    // padded index of element t + c*TT given pt = pad(t): when TT is a multiple of E the padding of the
+    // two terms separates, so the compiler sees base + compile-time constant (an immediate offset)
+    static DSC_DEV int pad_read(int t, int pt, int c) {
+        if constexpr (TT % E == 0) return pt + c * (TT + TT / E);
+        else return pad(t + c * TT);
+    }
     static_assert(STAGES <= 5, "FftArgs::tw / dsc_cuda_plan::tw1 hold 5 stage tables");
 };
 
@@ -108,15 +116,23 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
 #pragma unroll
                 for (int p = 0; p < R; ++p) v[b + p * NB] = r[p];
             } else {
+                // scatter to (j-k)*R + k + p*NS; p*NS is a multiple of E past the first stage, so its
+                // padding is a constant too
                 const int base = ((j - k) << LG_R) + k;
+                const int pbase = Sc::pad(base);
 #pragma unroll
-                for (int p = 0; p < R; ++p) sm[Sc::pad(base + p * NS)] = r[p];
+                for (int p = 0; p < R; ++p) {
+                    if constexpr (NS % E == 0) sm[pbase + p * (NS + NS / E)] = r[p];
+                    else if constexpr (NS == 1 && R == E) sm[pbase + p] = r[p];
+                    else sm[Sc::pad(base + p * NS)] = r[p];
+                }
             }
         }
         if constexpr (!LAST) {
             if (block_sync) __syncthreads(); else __syncwarp();
+            const int pt = Sc::pad(t);
 #pragma unroll
-            for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad(t + c * TT)];
+            for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
             if (block_sync) __syncthreads(); else __syncwarp();
             Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm, t, a, block_sync);
         }
@@ -128,6 +144,11 @@ template <typename T> DSC_DEV cx<T> four_step_twiddle(const FftArgs &a, const lo
     const cx<T> hi = __ldg((const cx<T> *)a.tw_hi + (int)(p >> a.four_shift));
     return cmul(lo, hi);
 }
+
+// Streaming accesses for the payload: each element is touched exactly once, so it should not
+// displace the twiddle tables from L1 / linger in L2 (ld.global.cs / st.global.cs).
+template <typename V> DSC_DEV V ld_stream(const V *p) { return __ldcs(p); }
+template <typename V> DSC_DEV void st_stream(V *p, const V v) { __stcs(p, v); }
 
 // Un-mix / mix step of the packed real transform for one bin pair (k, N-k).
 // Forward (dsc_fft.h:199-214 with c = -1/2, w = W_2N^k):   X[k], X[N-k] from Z[k], Z[N-k].
@@ -172,7 +193,12 @@ fft_lines(const FftArgs a) {
     V v[E];
 
     // ---------------------------------------------------------------- load
-    if (MODE == MODE_C2R) {
+    if (MODE == MODE_FAST) {
+        // every line of the block exists and is dense: a.x / a.out are (lines, N) row-major
+        const V *__restrict__ xp = (const V *)a.x + line * N + t;
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = ld_stream(xp + c * TT);
+    } else if (MODE == MODE_C2R) {
         // bins X[0..N] -> packed z[0..N); DC/Nyquist use real parts only (dsc_fft.h:227-228)
         const V *__restrict__ xc = (const V *)a.x + ibase;
         const V *__restrict__ twr = (const V *)a.tw_real;
@@ -250,7 +276,11 @@ fft_lines(const FftArgs a) {
     }
 
     // ---------------------------------------------------------------- store
-    if (MODE == MODE_C2C) {
+    if (MODE == MODE_FAST) {
+        V *__restrict__ op = (V *)a.out + line * N + t;
+#pragma unroll
+        for (int c = 0; c < E; ++c) st_stream(op + c * TT, v[c]);
+    } else if (MODE == MODE_C2C) {
         if (a.four_shift) {   // four-step first pass: times W_M^(in * k1)
 #pragma unroll
             for (int c = 0; c < E; ++c)

@@ -227,6 +227,10 @@ int run_fft(const dsc_cuda_plan *p, const void *x, bool x_real, void *out,
         set_stage_tables<T>(a, p->tw1);
         a.strided = inner > 1;
         a.do_scale = !FWD; a.scale = 1.0 / (double)n;
+        // dense last-axis lines in whole blocks take the bandwidth path
+        KernelEntry *fast = get_table<T, FWD, MODE_FAST, false>();
+        if (inner == 1 && !x_real && x_n == n && a.lines % fast[p->lg_n].lpb == 0)
+            return launch_lines(fast, p->lg_n, a, stream);
         return launch_lines(c2c_table<T, FWD>(inner > 1), p->lg_n, a, stream);
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis", n);

@@ -69,6 +69,8 @@ inline void __syncthreads() { pthread_barrier_wait(dsc_emul::tls.barrier); }
 // every call site is in block-uniform control flow, so a block barrier is a valid (stronger) stand-in
 inline void __syncwarp() { pthread_barrier_wait(dsc_emul::tls.barrier); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcs(const T *p) { return *p; }
+template <typename T> inline void __stcs(T *p, const T v) { *p = v; }
 
 inline void sincospi(double x, double *s, double *c) {
     const long double a = 3.14159265358979323846264338327950288L * (long double)x;
