@@ -7,6 +7,7 @@
 //       warp touches >= 64..128 contiguous bytes per access.
 #pragma once
 
+#include <cstdlib>
 #include <utility>
 #include "fft_kernels.cuh"
 
@@ -49,7 +50,7 @@ KernelEntry make_entry() {
     e.fn = fft_lines<T, LG_N, LG_E, LPB, FWD, MODE>;
     e.lpb = LPB;
     e.threads = LPB * Sc::TT;
-    e.smem = LPB * Sc::LINE * (int)sizeof(cx<T>);
+    e.smem = LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>)) * (int)sizeof(cx<T>);
     e.configured = false;
     return e;
 }
@@ -76,6 +77,56 @@ DSC_DECLARE_TABLE(double, true, MODE_R2C, false)  DSC_DECLARE_TABLE(double, fals
 DSC_DECLARE_TABLE(float, true, MODE_FAST, false)  DSC_DECLARE_TABLE(float, false, MODE_FAST, false)
 DSC_DECLARE_TABLE(double, true, MODE_FAST, false) DSC_DECLARE_TABLE(double, false, MODE_FAST, false)
 #undef DSC_DECLARE_TABLE
+
+// ---- fused four-step launches ------------------------------------------------------------------
+struct FusedEntry {
+    void (*fn)(const FftArgs, const FftArgs, const FourStepSync);
+    int lg_n1, lg_n2, threads, lpb_a, lpb_b, smem;
+    bool configured;
+};
+
+// block size for a pair of pass lengths: both passes keep >= 64 contiguous bytes per access
+template <typename T> constexpr int fused_threads(int lg_n1, int lg_n2) {
+    return (lg_n1 > 8 || lg_n2 > 8) ? 512 : 256;
+}
+
+template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_threads<T>(LG_N1, LG_N2)>
+FusedEntry make_fused() {
+    constexpr int LG_E1 = lg_e_for<T>(LG_N1), LG_E2 = lg_e_for<T>(LG_N2);
+    constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
+    constexpr int SM_A = LPB_A * Sched<LG_N1, LG_E1>::line_stride(LPB_A, (int)sizeof(cx<T>));
+    constexpr int SM_B = LPB_B * Sched<LG_N2, LG_E2>::line_stride(LPB_B, (int)sizeof(cx<T>));
+    FusedEntry e;
+    e.fn = four_step_fused<T, LG_N1, LG_N2, THREADS, FWD>;
+    e.lg_n1 = LG_N1; e.lg_n2 = LG_N2; e.threads = THREADS; e.lpb_a = LPB_A; e.lpb_b = LPB_B;
+    e.smem = (SM_A > SM_B ? SM_A : SM_B) * (int)sizeof(cx<T>);
+    e.configured = false;
+    return e;
+}
+
+// (lg_n1, lg_n2) pairs produced by plan_layout for lengths up to 2^20: lg_n2 = lg_n / 2, lg_n1 = lg_n - lg_n2
+#define DSC_FUSED_PAIRS(X) X(7, 7) X(8, 7) X(8, 8) X(9, 8) X(9, 9) X(10, 9) X(10, 10)
+
+// nullptr when the pair has no fused instantiation; defined in inst_*_fused.cu
+template <typename T, bool FWD> FusedEntry *fused_entry(int lg_n1, int lg_n2);
+template <> FusedEntry *fused_entry<float, true>(int, int);
+template <> FusedEntry *fused_entry<float, false>(int, int);
+template <> FusedEntry *fused_entry<double, true>(int, int);
+template <> FusedEntry *fused_entry<double, false>(int, int);
+
+#define DSC_DEFINE_FUSED(T, FWD)                                                           \
+    template <> FusedEntry *fused_entry<T, FWD>(int lg_n1, int lg_n2) {                    \
+        static FusedEntry table[] = {DSC_FUSED_PAIRS(DSC_FUSED_MAKE_##FWD##_##T)};         \
+        const char *pref = getenv("DSC_FUSED_THREADS");   /* tuning knob: 256 | 512 */         \
+        const int want = pref ? atoi(pref) : 0;                                            \
+        for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2 && (!want || e.threads == want)) return &e; \
+        for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
+        return nullptr;                                                                    \
+    }
+#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(), make_fused<float, true, A, B, 256>(),
+#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(), make_fused<float, false, A, B, 256>(),
+#define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B>(), make_fused<double, true, A, B, 256>(),
+#define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B>(), make_fused<double, false, A, B, 256>(),
 
 #define DSC_DEFINE_TABLE(T, FWD, MODE, SV)                                                        \
     template <> KernelEntry *get_table<T, FWD, MODE, SV>() {                                      \

@@ -33,6 +33,8 @@ enum Mode : int {
     MODE_C2R = 2,   // irfft: N+1 bins -> 2N reals, mixing fused before the first stage
     MODE_FAST = 3,  // dense complex lines (inner == 1, no pad/crop, whole blocks): the bandwidth path --
                     // one base pointer per thread, immediate offsets, streaming cache hints
+    MODE_PASS_A = 4,  // MODE_C2C as the first pass of the fused four-step kernel (payload in, L2 out)
+    MODE_PASS_B = 5,  // MODE_C2C/IN_ROWS as its second pass (L2 in, payload out)
 };
 
 // how MODE_C2C reads its input
@@ -68,6 +70,10 @@ struct FftArgs {
     long long go_pstride; // MODE_C2R: same, for the output
     int in_kind;          // InKind (MODE_C2C only)
     int strided;          // thread mapping: 1 = adjacent lines on adjacent lanes
+    int inner_shift;      // log2(inner) when inner is a power of two, else -1
+    int no_limit;         // every line exists and is read in full: skip the pad/crop predicates
+    long long ring_in;    // input / output row index taken modulo this (0 = off): ring of work rows
+    long long ring_out;
     double scale;         // applied to the outputs when do_scale (1/N of the inverse)
     int do_scale;
 };
@@ -78,8 +84,17 @@ template <int LG_N, int LG_E> struct Sched {
     static constexpr int TT = N / E;
     static constexpr int STAGES = LG_E == 0 ? 1 : (LG_N + LG_E - 1) / LG_E;
     static constexpr int lg_r(int s) { return (LG_N - s * LG_E) < LG_E ? (LG_N - s * LG_E) : LG_E; }
-    // padded length of one line in shared memory (+1 keeps adjacent lines on different banks)
-    static constexpr int LINE = N + (N >> LG_E) + 1;
+    // Padded length of one line in shared memory.  In the strided thread mapping adjacent lanes are
+    // adjacent LINES at the same position, and when fewer than a full bank phase of lines fit in a block
+    // the next lanes are the next position: the line stride must map (line, position) pairs of one phase
+    // (16 lanes of 8-byte elements, 8 lanes of 16-byte elements) onto distinct banks, i.e. be congruent
+    // to phase/LPB modulo the phase.
+    static __host__ __device__ constexpr int line_stride(int lpb, int elem_bytes) {
+        const int phase = 128 / elem_bytes;
+        const int want = lpb >= phase ? 1 : phase / lpb;
+        const int base = N + (N >> LG_E);
+        return base + ((want - base % phase) % phase + phase) % phase;
+    }
     static DSC_DEV int pad(int i) { return i + (i >> LG_E); }
     // padded index of element t + c*TT given pt = pad(t): when TT is a multiple of E the padding of the
     // two terms separates, so the compiler sees base + compile-time constant (an immediate offset)
@@ -90,6 +105,19 @@ template <int LG_N, int LG_E> struct Sched {
     static_assert(STAGES <= 5, "FftArgs::tw / dsc_cuda_plan::tw1 hold 5 stage tables");
 };
 
+// Barrier scope of the exchanges of one line.
+enum SyncKind : int { SYNC_WARP = 0, SYNC_BLOCK = 1, SYNC_LINE = 2 };
+struct LineSync {
+    int kind;     // SyncKind
+    int id;       // hardware barrier of this line (SYNC_LINE), 1..15
+    int count;    // threads of the line
+};
+DSC_DEV void line_sync(const LineSync &s) {
+    if (s.kind == SYNC_WARP) __syncwarp();
+    else if (s.kind == SYNC_BLOCK) __syncthreads();
+    else dsc_named_barrier(s.id, s.count);
+}
+
 template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
@@ -98,7 +126,7 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
     static constexpr int LG_NS = S * LG_E, NS = 1 << LG_NS;
     static constexpr bool LAST = (S == Sc::STAGES - 1);
 
-    static DSC_DEV void run(V (&v)[E], V *sm, const int t, const FftArgs &a, const bool block_sync) {
+    static DSC_DEV void run(V (&v)[E], V *sm, const int t, const FftArgs &a, const LineSync &ls) {
         const V *__restrict__ tw = (const V *)a.tw[S];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -129,19 +157,20 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
             }
         }
         if constexpr (!LAST) {
-            if (block_sync) __syncthreads(); else __syncwarp();
+            line_sync(ls);
             const int pt = Sc::pad(t);
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
-            if (block_sync) __syncthreads(); else __syncwarp();
-            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm, t, a, block_sync);
+            line_sync(ls);
+            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm, t, a, ls);
         }
     }
 };
 
-template <typename T> DSC_DEV cx<T> four_step_twiddle(const FftArgs &a, const long long p) {
-    const cx<T> lo = __ldg((const cx<T> *)a.tw_lo + (int)(p & a.four_mask));
-    const cx<T> hi = __ldg((const cx<T> *)a.tw_hi + (int)(p >> a.four_shift));
+// W_M^p from the two sqrt(M)-sized tables; p = n2 * k1 < M <= 2^30 fits 32 bits
+template <typename T> DSC_DEV cx<T> four_step_twiddle(const FftArgs &a, const unsigned p) {
+    const cx<T> lo = __ldg((const cx<T> *)a.tw_lo + (p & (unsigned)a.four_mask));
+    const cx<T> hi = __ldg((const cx<T> *)a.tw_hi + (p >> a.four_shift));
     return cmul(lo, hi);
 }
 
@@ -163,42 +192,120 @@ DSC_DEV void real_pair(const cx<T> a, const cx<T> b, const cx<T> w_fwd, cx<T> &r
     rb = mk<T>(h1r - wr * h2r + wi * h2i, -h1i + wr * h2i + wi * h2r);
 }
 
+// Payload access with a compile-time cache policy.
+enum CachePol : int { POL_DEFAULT = 0, POL_STREAM = 1, POL_L2 = 2 };
+template <int POL, typename V> DSC_DEV V ld_pol(const V *p) {
+    if constexpr (POL == POL_STREAM) return __ldcs(p);
+    else if constexpr (POL == POL_L2) return __ldcg(p);      // coherent at L2: data another SM just produced
+    else return *p;
+}
+template <int POL, typename V> DSC_DEV void st_pol(V *p, const V v) {
+    if constexpr (POL == POL_STREAM) __stcs(p, v);
+    else *p = v;
+}
+
+// Body of one thread block: LPB lines starting at line `block * LPB`.
 // THREADS = LPB * TT.  Dynamic shared memory: LPB * Sched::LINE * sizeof(cx<T>).
 template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
-__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)))
-fft_lines(const FftArgs a) {
+DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned char *smem_raw) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
     constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, THREADS = LPB * TT;
     constexpr int PAIRS = E > 1 ? E / 2 : 1;   // bin pairs per thread in the real modes
-    DSC_DYN_SMEM(smem_raw);
+    constexpr bool IS_C2C = MODE == MODE_C2C || MODE == MODE_PASS_A || MODE == MODE_PASS_B;
+    // four-step passes: the payload streams through once, the intermediate is L2-to-L2 traffic
+    constexpr int POL_IN = MODE == MODE_PASS_A ? POL_STREAM : MODE == MODE_PASS_B ? POL_L2 : POL_DEFAULT;
+    constexpr int POL_OUT = MODE == MODE_PASS_B ? POL_STREAM : POL_DEFAULT;
     V *sm_all = (V *)smem_raw;
 
+    constexpr bool TILED = MODE == MODE_PASS_A || MODE == MODE_PASS_B;   // cooperative tile staging
     const int tid = threadIdx.x;
     int l, t;
-    if (a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
-    V *sm = sm_all + l * Sc::LINE;
-    // warp-level barriers suffice only when every line lives inside one warp
-    const bool block_sync = a.strided || TT > 32;
+    if (!TILED && a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
+    constexpr int LINE = Sc::line_stride(LPB, (int)sizeof(V));
+    V *sm = sm_all + l * LINE;
+    // A line's exchanges need: a warp barrier when the line lives inside one warp; its own hardware
+    // barrier when it is a whole number of warps and the block has few enough lines (lines then
+    // progress independently of each other); otherwise the block barrier.
+    LineSync ls;
+    ls.id = 1 + l; ls.count = TT;
+    if (!TILED && a.strided) ls.kind = SYNC_BLOCK;
+    else if (TT <= 32) ls.kind = SYNC_WARP;
+    else if (TILED && LPB <= 15 && TT % 32 == 0) ls.kind = SYNC_LINE;
+    else ls.kind = SYNC_BLOCK;
 
-    const long long line = (long long)blockIdx.x * LPB + l;
+    const long long line = block * LPB + l;
     const bool active = line < a.lines;
-    const long long o = active ? line / a.inner : 0;
-    const long long in = active ? line % a.inner : 0;
-    const long long ibase = o * a.gi.ostride + in * a.gi.lstride;
-    const long long obase = o * a.go.ostride + in * a.go.lstride;
-    const long long lim = active ? a.in_limit - in * a.gi.lstride : 0;   // read iff offset < lim
+    long long o = 0, in = 0;
+    if (active) {
+        if (a.inner_shift >= 0) { o = line >> a.inner_shift; in = line & ((1LL << a.inner_shift) - 1); }
+        else { o = line / a.inner; in = line - o * a.inner; }
+    }
+    const long long o_in = a.ring_in ? o % a.ring_in : o;
+    const long long o_out = a.ring_out ? o % a.ring_out : o;
+    const long long ibase = o_in * a.gi.ostride + in * a.gi.lstride;
+    const long long obase = o_out * a.go.ostride + in * a.go.lstride;
+    // element offsets are t*estride + c*(TT*estride): one multiply per thread, then additions
+    const long long ioff0 = (long long)t * a.gi.estride, istep = (long long)TT * a.gi.estride;
+    const long long ooff0 = (long long)t * a.go.estride, ostep = (long long)TT * a.go.estride;
+    // read iff offset < lim; "no limit" (dense lines) is encoded as a huge lim by the host
+    const long long lim = active ? a.in_limit - in * a.gi.lstride : 0;
     const V zero = mk<T>((T)0, (T)0);
+    // cooperative tile copies (TILED): lane = line within the tile, then position; each thread moves E
+    // elements at positions p0 + c*TT of line lt.  The fused launch guarantees whole tiles inside one row.
+    const int lt = tid % LPB, p0 = tid / LPB;
+    long long tile_o = 0, tile_in0 = 0;
+    if constexpr (TILED) {
+        const long long line0 = block * LPB;
+        tile_o = line0 >> a.inner_shift;
+        tile_in0 = line0 & ((1LL << a.inner_shift) - 1);
+    }
 
     V v[E];
 
     // ---------------------------------------------------------------- load
-    if (MODE == MODE_FAST) {
+    if constexpr (MODE == MODE_FAST) {
         // every line of the block exists and is dense: a.x / a.out are (lines, N) row-major
         const V *__restrict__ xp = (const V *)a.x + line * N + t;
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = ld_stream(xp + c * TT);
-    } else if (MODE == MODE_C2R) {
+    } else if constexpr (MODE == MODE_PASS_A) {
+        // strided source tile -> shared memory (adjacent lanes = adjacent lines = contiguous bytes)
+        const long long row_in = a.ring_in ? tile_o % a.ring_in : tile_o;
+        const long long sbase = row_in * a.gi.ostride + (tile_in0 + lt) * a.gi.lstride + (long long)p0 * a.gi.estride;
+        const long long tlim = a.in_limit - (tile_in0 + lt) * a.gi.lstride - (long long)p0 * a.gi.estride;
+        V *dst = sm_all + lt * LINE;
+        const int pp0 = Sc::pad(p0);
+        if (a.in_kind == IN_COMPLEX) {
+            const V *__restrict__ src = (const V *)a.x + sbase;
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                dst[Sc::pad_read(p0, pp0, c)] = (a.no_limit || c * istep < tlim) ? ld_pol<POL_IN>(src + c * istep) : zero;
+        } else if (a.in_kind == IN_REAL) {
+            const T *__restrict__ src = (const T *)a.x + sbase;
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                dst[Sc::pad_read(p0, pp0, c)] = mk<T>(c * istep < tlim ? ld_pol<POL_IN>(src + c * istep) : (T)0, (T)0);
+        } else {  // IN_PAIRS
+            const T *__restrict__ src = (const T *)a.x + sbase;
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const T re = c * istep < tlim ? ld_pol<POL_IN>(src + c * istep) : (T)0;
+                const T im = c * istep + a.gi_pstride < tlim ? ld_pol<POL_IN>(src + c * istep + a.gi_pstride) : (T)0;
+                dst[Sc::pad_read(p0, pp0, c)] = mk<T>(re, im);
+            }
+        }
+        __syncthreads();
+        const int pt = Sc::pad(t);
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
+        line_sync(ls);
+    } else if constexpr (MODE == MODE_PASS_B) {
+        // contiguous work rows straight into registers (written a moment ago by other SMs: L2 loads)
+        const V *__restrict__ xp = (const V *)a.x + ibase + t;
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = ld_pol<POL_IN>(xp + c * TT);
+    } else if constexpr (MODE == MODE_C2R) {
         // bins X[0..N] -> packed z[0..N); DC/Nyquist use real parts only (dsc_fft.h:227-228)
         const V *__restrict__ xc = (const V *)a.x + ibase;
         const V *__restrict__ twr = (const V *)a.tw_real;
@@ -221,53 +328,61 @@ fft_lines(const FftArgs a) {
             }
         }
         __syncthreads();
+        const int pt = Sc::pad(t);
 #pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad(t + c * TT)];
+        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
         __syncthreads();
     } else if (MODE == MODE_R2C || a.in_kind == IN_PAIRS) {
         // 2N reals seen as N complex: z[j] = (x[..2j], x[..2j+1]); gi is in REAL elements
         const T *__restrict__ xr = (const T *)a.x + ibase;
 #pragma unroll
         for (int c = 0; c < E; ++c) {
-            const long long off = (long long)(t + c * TT) * a.gi.estride;
-            const T re = off < lim ? xr[off] : (T)0;
-            const T im = off + a.gi_pstride < lim ? xr[off + a.gi_pstride] : (T)0;
+            const long long off = ioff0 + c * istep;
+            const T re = off < lim ? ld_pol<POL_IN>(xr + off) : (T)0;
+            const T im = off + a.gi_pstride < lim ? ld_pol<POL_IN>(xr + off + a.gi_pstride) : (T)0;
             v[c] = mk<T>(re, im);
         }
     } else if (a.in_kind == IN_REAL) {
         const T *__restrict__ xr = (const T *)a.x + ibase;
 #pragma unroll
         for (int c = 0; c < E; ++c) {
-            const long long off = (long long)(t + c * TT) * a.gi.estride;
-            v[c] = mk<T>(off < lim ? xr[off] : (T)0, (T)0);
+            const long long off = ioff0 + c * istep;
+            v[c] = mk<T>(off < lim ? ld_pol<POL_IN>(xr + off) : (T)0, (T)0);
         }
     } else if (a.in_kind == IN_COMPLEX) {
-        const V *__restrict__ xc = (const V *)a.x + ibase;
+        const V *__restrict__ xc = (const V *)a.x + ibase + ioff0;
+        if (a.no_limit) {       // dense lines, whole blocks: no predicates
 #pragma unroll
-        for (int c = 0; c < E; ++c) {
-            const long long off = (long long)(t + c * TT) * a.gi.estride;
-            v[c] = off < lim ? xc[off] : zero;
+            for (int c = 0; c < E; ++c) v[c] = ld_pol<POL_IN>(xc + c * istep);
+        } else {
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = (ioff0 + c * istep) < lim ? ld_pol<POL_IN>(xc + c * istep) : zero;
         }
-    } else {  // IN_ROWS: LPB rows loaded cooperatively (coalesced along the row), then picked up per line
-        const long long line0 = (long long)blockIdx.x * LPB;
-        for (int e = tid; e < LPB * N; e += THREADS) {
-            const int row = e / N, pos = e % N;
-            const long long rl = line0 + row;
-            V val = zero;
-            if (rl < a.lines) {
-                const long long ro = rl / a.inner, rin = rl % a.inner;
-                val = ((const V *)a.x)[ro * a.gi.ostride + rin * a.gi.lstride + (long long)pos * a.gi.estride];
-            }
-            sm_all[row * Sc::LINE + Sc::pad(pos)] = val;
+    } else {
+        // IN_ROWS: the block's LPB rows are loaded cooperatively, coalesced along each row, then every
+        // thread picks up the points of its own line.  Row addresses advance without divisions.
+        const long long line0 = block * LPB;
+        long long ro, rin;
+        if (a.inner_shift >= 0) { ro = line0 >> a.inner_shift; rin = line0 & ((1LL << a.inner_shift) - 1); }
+        else { ro = line0 / a.inner; rin = line0 - ro * a.inner; }
+        for (int row = 0; row < LPB; ++row) {
+            const bool row_ok = line0 + row < a.lines;
+            const long long ro_in = a.ring_in ? ro % a.ring_in : ro;
+            const V *__restrict__ src = (const V *)a.x + ro_in * a.gi.ostride + rin * a.gi.lstride;
+            V *dst = sm_all + row * LINE;
+            for (int pos = tid; pos < N; pos += THREADS)
+                dst[Sc::pad(pos)] = row_ok ? ld_pol<POL_IN>(src + (long long)pos * a.gi.estride) : zero;
+            if (++rin == a.inner) { rin = 0; ++ro; }
         }
         __syncthreads();
+        const int pt = Sc::pad(t);
 #pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad(t + c * TT)];
+        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
         __syncthreads();
     }
 
     // ---------------------------------------------------------------- transform
-    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, t, a, block_sync);
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, t, a, ls);
 
     if (a.do_scale) {
         const T s = (T)a.scale;
@@ -276,36 +391,56 @@ fft_lines(const FftArgs a) {
     }
 
     // ---------------------------------------------------------------- store
-    if (MODE == MODE_FAST) {
+    if constexpr (MODE == MODE_FAST) {
         V *__restrict__ op = (V *)a.out + line * N + t;
 #pragma unroll
         for (int c = 0; c < E; ++c) st_stream(op + c * TT, v[c]);
-    } else if (MODE == MODE_C2C) {
-        if (a.four_shift) {   // four-step first pass: times W_M^(in * k1)
+    } else if constexpr (TILED) {
+        if (MODE == MODE_PASS_A && a.four_shift) {   // times W_M^(n2 * k1), n2 = this line's column
+            const unsigned q = (unsigned)in;
 #pragma unroll
             for (int c = 0; c < E; ++c)
-                v[c] = cmul_tw<FWD>(v[c], four_step_twiddle<T>(a, in * (long long)(t + c * TT)));
+                v[c] = cmul_tw<FWD>(v[c], four_step_twiddle<T>(a, q * (unsigned)(t + c * TT)));
+        }
+        // registers -> shared memory (own line), then the block stores the tile with adjacent lanes on
+        // adjacent lines: contiguous LPB*sizeof(V) bytes per position
+        const int pt = Sc::pad(t);
+#pragma unroll
+        for (int c = 0; c < E; ++c) sm[Sc::pad_read(t, pt, c)] = v[c];
+        __syncthreads();
+        const long long row_out = a.ring_out ? tile_o % a.ring_out : tile_o;
+        V *__restrict__ op = (V *)a.out + row_out * a.go.ostride + (tile_in0 + lt) * a.go.lstride + (long long)p0 * a.go.estride;
+        const V *src = sm_all + lt * LINE;
+        const int pp0 = Sc::pad(p0);
+#pragma unroll
+        for (int c = 0; c < E; ++c) st_pol<POL_OUT>(op + c * ostep, src[Sc::pad_read(p0, pp0, c)]);
+    } else if constexpr (IS_C2C) {
+        if (a.four_shift) {   // four-step first pass: times W_M^(in * k1)
+            const unsigned q = (unsigned)in;
+#pragma unroll
+            for (int c = 0; c < E; ++c)
+                v[c] = cmul_tw<FWD>(v[c], four_step_twiddle<T>(a, q * (unsigned)(t + c * TT)));
         }
         if (active) {
-            V *__restrict__ oc = (V *)a.out + obase;
+            V *__restrict__ oc = (V *)a.out + obase + ooff0;
 #pragma unroll
-            for (int c = 0; c < E; ++c) oc[(long long)(t + c * TT) * a.go.estride] = v[c];
+            for (int c = 0; c < E; ++c) st_pol<POL_OUT>(oc + c * ostep, v[c]);
         }
-    } else if (MODE == MODE_C2R) {
+    } else if constexpr (MODE == MODE_C2R) {
         // N complex = 2N reals; go is in REAL elements
         if (active) {
-            T *__restrict__ orl = (T *)a.out + obase;
+            T *__restrict__ orl = (T *)a.out + obase + ooff0;
 #pragma unroll
             for (int c = 0; c < E; ++c) {
-                const long long off = (long long)(t + c * TT) * a.go.estride;
-                orl[off] = v[c].x;
-                orl[off + a.go_pstride] = v[c].y;
+                orl[c * ostep] = v[c].x;
+                orl[c * ostep + a.go_pstride] = v[c].y;
             }
         }
     } else {  // MODE_R2C: Z -> shared memory, then each thread un-mixes its bin pairs
         __syncthreads();
+        const int pt = Sc::pad(t);
 #pragma unroll
-        for (int c = 0; c < E; ++c) sm[Sc::pad(t + c * TT)] = v[c];
+        for (int c = 0; c < E; ++c) sm[Sc::pad_read(t, pt, c)] = v[c];
         __syncthreads();
         if (active) {
             V *__restrict__ oc = (V *)a.out + obase;
@@ -330,6 +465,87 @@ fft_lines(const FftArgs a) {
                 }
             }
         }
+    }
+}
+
+template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
+__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)))
+fft_lines(const FftArgs a) {
+    DSC_DYN_SMEM(smem_raw);
+    fft_lines_body<T, LG_N, LG_E, LPB, FWD, MODE>(a, (long long)blockIdx.x, smem_raw);
+}
+
+// ------------------------------------------------------------------------------------------
+// Four-step transform n = n1*n2 as ONE launch.
+//
+// Per top-level line ("row") there are TA first-pass blocks (length-n1 transforms over stride-n2
+// data, times W_n^(n2 k1), into a ring of work rows) and TB second-pass blocks (length-n2 transforms
+// of contiguous work rows, stored with stride n1).  Blocks take a ticket when they start; ticket
+// order is row-major with a row's A blocks before its B blocks, so a block only ever waits for
+// blocks with SMALLER tickets, which are already running -- no deadlock whatever the dispatch
+// order.  A B block waits until all TA A blocks of its row have published; an A block that reuses a
+// ring slot waits until the B blocks of the row that last used it are done.  The intermediate of a
+// row is therefore consumed a few microseconds after it is produced and never leaves L2
+// (POL_L2 loads bypass the non-coherent L1; the payload itself streams with evict-first hints),
+// so HBM sees one read and one write per element although there are two passes.
+struct FourStepSync {
+    unsigned *ticket;    // one counter
+    unsigned *a_done;    // per row: first-pass blocks finished
+    unsigned *b_done;    // per row: second-pass blocks finished
+    int tiles_a, tiles_b;
+    int ring;            // work rows (0 = one work row per top-level row, no reuse)
+    int rows;
+    int lag;             // ticket order: the B blocks of row r come after the A blocks of row r + lag, so
+                         // that in steady state a B block finds its row already complete and never spins
+};
+
+DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
+    const volatile unsigned *c = counter;
+    while (*c < target) __nanosleep(64);
+    __threadfence();
+}
+
+template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
+__global__ void __launch_bounds__(THREADS)
+four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
+    constexpr int LG_E1 = LG_N1 < (sizeof(T) == 4 ? 4 : 3) ? LG_N1 : (sizeof(T) == 4 ? 4 : 3);
+    constexpr int LG_E2 = LG_N2 < (sizeof(T) == 4 ? 4 : 3) ? LG_N2 : (sizeof(T) == 4 ? 4 : 3);
+    constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
+    static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
+    DSC_DYN_SMEM(smem_raw);
+    __shared__ unsigned ticket_s;
+    if (threadIdx.x == 0) ticket_s = atomicAdd(s.ticket, 1u);
+    __syncthreads();
+    // ticket -> (role, row, tile): A(0..lag-1), then groups { A(i + lag), B(i) }, then the last B rows
+    const unsigned ta = (unsigned)s.tiles_a, tb = (unsigned)s.tiles_b, lag = (unsigned)s.lag;
+    unsigned ticket = ticket_s, row, r;
+    bool role_a;
+    if (ticket < lag * ta) { role_a = true; row = ticket / ta; r = ticket % ta; }
+    else {
+        ticket -= lag * ta;
+        const unsigned full = (unsigned)s.rows - lag;
+        if (ticket < full * (ta + tb)) {
+            const unsigned i = ticket / (ta + tb), w = ticket % (ta + tb);
+            if (w < ta) { role_a = true; row = i + lag; r = w; } else { role_a = false; row = i; r = w - ta; }
+        } else {
+            ticket -= full * (ta + tb);
+            role_a = false; row = full + ticket / tb; r = ticket % tb;
+        }
+    }
+    if (role_a) {
+        if (s.ring && row >= (unsigned)s.ring) {
+            if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
+            __syncthreads();
+        }
+        fft_lines_body<T, LG_N1, LG_E1, LPB_A, FWD, MODE_PASS_A>(a, (long long)row * s.tiles_a + r, smem_raw);
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(s.a_done + row, 1u); }
+    } else {
+        if (threadIdx.x == 0) spin_until(s.a_done + row, (unsigned)s.tiles_a);
+        __syncthreads();
+        fft_lines_body<T, LG_N2, LG_E2, LPB_B, FWD, MODE_PASS_B>(b, (long long)row * s.tiles_b + r, smem_raw);
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(s.b_done + row, 1u); }
     }
 }
 

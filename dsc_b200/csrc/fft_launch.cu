@@ -145,7 +145,9 @@ int build_tables(dsc_cuda_plan *p, const PlanLayout &L, void *stream) {
 
 // ---- launches --------------------------------------------------------------------------
 
-int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a, void *stream) {
+inline int pow2_shift(long long v);
+
+int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a_in, void *stream) {
     KernelEntry &e = table[lg_n];
 #if !defined(DSC_EMUL)
     if (!e.configured) {
@@ -157,7 +159,10 @@ int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a, void *stream) {
         e.configured = true;
     }
 #endif
-    if (a.lines <= 0) return 0;
+    if (a_in.lines <= 0) return 0;
+    FftArgs a = a_in;
+    a.inner_shift = pow2_shift(a.inner);
+    if (a.lines % e.lpb != 0) a.no_limit = 0;
     const long long blocks = (a.lines + e.lpb - 1) / e.lpb;
     if (blocks > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "too many lines for one grid: %lld", a.lines);
     DSC_LAUNCH(e.fn, (unsigned)blocks, e.threads, e.smem, stream, a);
@@ -174,18 +179,32 @@ KernelEntry *c2c_table(bool strided_shape) {
     return strided_shape ? get_table<T, FWD, MODE_C2C, true>() : get_table<T, FWD, MODE_C2C, false>();
 }
 
-// The two passes of the four-step decomposition n = n1*n2 of `rows` contiguous lines:
+inline int pow2_shift(long long v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((1LL << s) < v) ++s;
+    return s;
+}
+
+inline size_t in_elem_size(const FftArgs &a, size_t real_size) {
+    return (a.in_kind == IN_REAL || a.in_kind == IN_PAIRS) ? real_size : 2 * real_size;
+}
+
+// The two passes of the four-step decomposition n = n1*n2 of `rows` lines:
 //   A: for every n2, length-n1 transform over stride-n2 data, times W_n^(n2 k1) -> work[row][k1][n2]
 //   B: for every k1, length-n2 transform of the contiguous run work[row][k1][:] -> dst[row][k1 + n1 k2]
-// `src` geometry (element kind, row stride, limit) comes in through `first`.
+// `first` carries the source geometry of pass A (element kind, row stride = gi.ostride, limit).
+// Preferred: ONE fused launch with a ring of work rows that stays in L2 (four_step_fused).  Shapes the
+// fused kernel does not cover fall back to two launches per chunk of rows.
 template <typename T, bool FWD>
-int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
+int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work, size_t work_bytes,
               void *dst, long long dst_row_stride, bool scale, void *stream) {
+    using V = cx<T>;
     const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
-    // pass A
+    const size_t row_bytes = (size_t)n * sizeof(V);
+    if (rows <= 0) return 0;
+
     FftArgs a = first;
-    a.out = work;
-    a.lines = rows * n2;
     a.inner = n2;
     a.go = LineGeom{n, 1, n2};
     set_stage_tables<T>(a, p->tw1);
@@ -193,12 +212,8 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
     a.four_shift = p->four_shift; a.four_mask = (1 << p->four_shift) - 1;
     a.strided = 1;
     a.do_scale = 0;
-    int rc = launch_lines(c2c_table<T, FWD>(true), p->lg_n1, a, stream);
-    if (rc) return rc;
-    // pass B
+
     FftArgs b{};
-    b.x = work; b.out = dst;
-    b.lines = rows * n1;
     b.inner = n1;
     b.gi = LineGeom{n, n2, 1};
     b.go = LineGeom{dst_row_stride, 1, n1};
@@ -207,7 +222,77 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
     set_stage_tables<T>(b, p->tw2);
     b.strided = 1;
     b.do_scale = scale; b.scale = 1.0 / (double)n;
-    return launch_lines(c2c_table<T, FWD>(true), p->lg_n2, b, stream);
+
+    FusedEntry *fe = fused_entry<T, FWD>(p->lg_n1, p->lg_n2);
+    const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
+    if (fe != nullptr && rows * (n2 / fe->lpb_a + n1 / fe->lpb_b) < 0x7fffffffLL &&
+        work != nullptr && work_bytes >= sync_bytes + row_bytes) {
+        // ring of work rows: as many as fit, but no more than keeps the intermediate inside L2
+        const size_t l2_budget = 64u << 20;
+        long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
+        const long long cap = (long long)(l2_budget / row_bytes) > 4 ? (long long)(l2_budget / row_bytes) : 4;
+        if (ring > cap) ring = cap;
+        if (ring >= rows) ring = 0;
+        FourStepSync s{};
+        s.ticket = (unsigned *)work;
+        s.a_done = s.ticket + 1;
+        s.b_done = s.a_done + rows;
+        s.tiles_a = (int)(n2 / fe->lpb_a);
+        s.tiles_b = (int)(n1 / fe->lpb_b);
+        s.ring = (int)ring;
+        s.rows = (int)rows;
+        // lag (in rows) between a row's first and second pass in ticket order: about two grids' worth of
+        // resident blocks, so second-pass blocks start on rows that are already complete; below the ring
+        {
+            const long long resident = 148LL * (2048 / fe->threads);
+            long long lag = (2 * resident + s.tiles_a + s.tiles_b - 1) / (s.tiles_a + s.tiles_b);
+            if (lag < 1) lag = 1;
+            // ... and at most half the ring, so a first-pass block that reuses a work row finds the
+            // second pass of its previous owner long finished instead of spinning on it
+            if (ring > 0 && lag > ring / 2) lag = ring / 2;
+            if (lag > rows) lag = rows;
+            s.lag = (int)lag;
+        }
+        V *mid = (V *)((char *)work + sync_bytes);
+        a.out = mid; a.lines = rows * n2; a.ring_out = ring; a.inner_shift = p->lg_n2;
+        a.no_limit = first.in_limit >= n;        // whole blocks by construction (n2 % lpb_a == 0)
+        b.x = mid; b.out = dst; b.lines = rows * n1; b.ring_in = ring; b.inner_shift = p->lg_n1;
+#if defined(DSC_EMUL)
+        memset(work, 0, sync_bytes);
+#else
+        if (!fe->configured) {
+            if (fe->smem > 48 * 1024) {
+                const cudaError_t err = cudaFuncSetAttribute((const void *)fe->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fe->smem);
+                if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
+            }
+            fe->configured = true;
+        }
+        const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
+        if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
+#endif
+        const unsigned blocks = (unsigned)(rows * (s.tiles_a + s.tiles_b));
+        DSC_LAUNCH(fe->fn, blocks, fe->threads, fe->smem, stream, a, b, s);
+        return check_launch("four_step_fused");
+    }
+
+    // two launches per chunk of rows
+    if (!work || work_bytes < row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (n=%lld)", n);
+    const long long chunk = (long long)(work_bytes / row_bytes);
+    const size_t in_es = in_elem_size(first, sizeof(T));
+    for (long long r0 = 0; r0 < rows; r0 += chunk) {
+        const long long nr = rows - r0 < chunk ? rows - r0 : chunk;
+        a.x = (const char *)first.x + (size_t)r0 * (size_t)first.gi.ostride * in_es;
+        a.out = work;
+        a.lines = nr * n2;
+        int rc = launch_lines(c2c_table<T, FWD>(true), p->lg_n1, a, stream);
+        if (rc) return rc;
+        b.x = work;
+        b.out = (V *)dst + (size_t)r0 * (size_t)dst_row_stride;
+        b.lines = nr * n1;
+        rc = launch_lines(c2c_table<T, FWD>(true), p->lg_n2, b, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 template <typename T, bool FWD>
@@ -234,21 +319,12 @@ int run_fft(const dsc_cuda_plan *p, const void *x, bool x_real, void *out,
         return launch_lines(c2c_table<T, FWD>(inner > 1), p->lg_n, a, stream);
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis", n);
-    const size_t row_bytes = (size_t)n * sizeof(cx<T>);
-    if (!work || work_bytes < row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (n=%lld)", n);
-    const long long chunk = (long long)(work_bytes / row_bytes);
-    for (long long r0 = 0; r0 < outer; r0 += chunk) {
-        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
-        FftArgs a{};
-        const size_t in_es = x_real ? sizeof(T) : sizeof(cx<T>);
-        a.x = (const char *)x + (size_t)r0 * x_n * in_es;
-        a.gi = LineGeom{(long long)x_n, 1, 1LL << p->lg_n2};
-        a.in_limit = take;
-        a.in_kind = x_real ? IN_REAL : IN_COMPLEX;
-        const int rc = four_step<T, FWD>(p, a, rows, work, (char *)out + (size_t)r0 * row_bytes, n, !FWD, stream);
-        if (rc) return rc;
-    }
-    return 0;
+    FftArgs a{};
+    a.x = x;
+    a.gi = LineGeom{(long long)x_n, 1, 1LL << p->lg_n2};
+    a.in_limit = take;
+    a.in_kind = x_real ? IN_REAL : IN_COMPLEX;
+    return four_step<T, FWD>(p, a, outer, work, work_bytes, out, n, !FWD, stream);
 }
 
 template <typename T>
@@ -272,30 +348,22 @@ int run_rfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, 
         return launch_lines(get_table<T, true, MODE_R2C, false>(), p->lg_n, a, stream);
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass rfft (order %lld) along a strided axis", n);
-    const size_t row_bytes = (size_t)n * sizeof(V);
-    if (!work || work_bytes < row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
-    const long long chunk = (long long)(work_bytes / row_bytes);
-    for (long long r0 = 0; r0 < outer; r0 += chunk) {
-        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
-        FftArgs a{};
-        a.x = (const T *)x + (size_t)r0 * x_n;
-        a.gi = LineGeom{(long long)x_n, 2, 2LL << p->lg_n2};     // REAL elements
-        a.gi_pstride = 1;
-        a.in_limit = take;
-        a.in_kind = IN_PAIRS;
-        V *dst = (V *)out + (size_t)r0 * (n + 1);
-        int rc = four_step<T, true>(p, a, rows, work, dst, n + 1, false, stream);
-        if (rc) return rc;
-        const long long items = rows * (n / 2);
-        const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
-        auto mix = real_mix_rows<true, T>;
-        DSC_LAUNCH(mix, blocks, 256, 0, stream, (const V *)nullptr, dst, rows, (int)n,
-                   (long long)0, 0, (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift,
-                   (1 << p->real_shift) - 1);
-        rc = check_launch("real_mix_rows");
-        if (rc) return rc;
-    }
-    return 0;
+    // packed complex transform into the bin rows (stride n+1), then un-mix the bin pairs in place
+    FftArgs a{};
+    a.x = x;
+    a.gi = LineGeom{(long long)x_n, 2, 2LL << p->lg_n2};     // REAL elements
+    a.gi_pstride = 1;
+    a.in_limit = take;
+    a.in_kind = IN_PAIRS;
+    int rc = four_step<T, true>(p, a, outer, work, work_bytes, out, n + 1, false, stream);
+    if (rc) return rc;
+    const long long items = outer * (n / 2);
+    const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+    auto mix = real_mix_rows<true, T>;
+    DSC_LAUNCH(mix, blocks, 256, 0, stream, (const V *)nullptr, (V *)out, outer, (int)n,
+               (long long)0, 0, (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift,
+               (1 << p->real_shift) - 1);
+    return check_launch("real_mix_rows");
 }
 
 template <typename T>
@@ -320,14 +388,16 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
         return launch_lines(get_table<T, false, MODE_C2R, false>(), p->lg_n, a, stream);
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass irfft (order %lld) along a strided axis", n);
-    // work = [ packed z rows | four-step intermediate ], both rows x n complex
+    // work = [ packed z rows of the chunk | four-step work ]
     const size_t row_bytes = (size_t)n * sizeof(V);
-    if (!work || work_bytes < 2 * row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
-    const long long chunk = (long long)(work_bytes / (2 * row_bytes));
+    if (!work || work_bytes < 2 * row_bytes + 4096) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
+    long long chunk = (long long)((work_bytes / 2) / row_bytes);
+    if (chunk > outer) chunk = outer;
+    V *z = (V *)work;
+    char *fs_work = (char *)work + align_up((size_t)chunk * row_bytes, 256);
+    const size_t fs_bytes = work_bytes - (size_t)(fs_work - (char *)work);
     for (long long r0 = 0; r0 < outer; r0 += chunk) {
         const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
-        V *z = (V *)work;
-        V *mid = z + (size_t)rows * n;
         const long long items = rows * (n / 2);
         const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
         auto mix = real_mix_rows<false, T>;
@@ -341,7 +411,7 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
         a.gi = LineGeom{n, 1, 1LL << p->lg_n2};
         a.in_limit = n;
         a.in_kind = IN_COMPLEX;
-        rc = four_step<T, false>(p, a, rows, mid, (V *)out + (size_t)r0 * n, n, true, stream);
+        rc = four_step<T, false>(p, a, rows, fs_work, fs_bytes, (V *)out + (size_t)r0 * n, n, true, stream);
         if (rc) return rc;
     }
     return 0;
@@ -394,9 +464,16 @@ int dsc_cuda_plan_build(dsc_cuda_plan *plan, int n, int fft_type, int dtype,
 
 size_t dsc_cuda_work_bytes(const dsc_cuda_plan *plan, int64_t lines) {
     if (!plan_ok(plan) || plan->lg_n2 == 0 || lines <= 0) return 0;
+    // ring of work rows that stays in L2 (at least 4 rows), plus the per-row flags of the fused launch;
+    // REAL plans also stage the packed spectrum of the rows in flight (irfft)
     const size_t es = plan->dtype == DSC_CUDA_F64 ? sizeof(double2) : sizeof(float2);
-    const size_t per_line = (size_t)plan->n * es * (plan->fft_type == DSC_CUDA_FFT_REAL ? 2 : 1);
-    return per_line * (size_t)lines;
+    const size_t row = (size_t)plan->n * es;
+    size_t ring = (64u << 20) / row > 4 ? (64u << 20) / row : 4;
+    if (ring > (size_t)lines) ring = (size_t)lines;
+    const size_t sync = align_up((size_t)(1 + 2 * lines) * sizeof(unsigned), 256);
+    size_t total = sync + ring * row + 256;
+    if (plan->fft_type == DSC_CUDA_FFT_REAL) total = 2 * total + 4096;
+    return total;
 }
 
 int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *out,

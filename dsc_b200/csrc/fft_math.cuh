@@ -19,6 +19,15 @@ namespace dscfft {
 
 #define DSC_DEV __device__ __forceinline__
 
+// bar.sync on one of the 16 hardware barriers for a subset of the block's warps
+#if defined(DSC_EMUL)
+#define dsc_named_barrier(id, count) __syncthreads()   /* every line runs the same sequence: a block barrier is equivalent */
+#else
+__device__ __forceinline__ void dsc_named_barrier(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+#endif
+
 // dynamic shared memory of the running block
 #if defined(DSC_EMUL)
 #define DSC_DYN_SMEM(name) unsigned char *name = dsc_emul::tls.smem

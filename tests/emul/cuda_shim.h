@@ -70,6 +70,11 @@ inline void __syncthreads() { pthread_barrier_wait(dsc_emul::tls.barrier); }
 inline void __syncwarp() { pthread_barrier_wait(dsc_emul::tls.barrier); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+#define __shared__ static
 template <typename T> inline void __stcs(T *p, const T v) { *p = v; }
 
 inline void sincospi(double x, double *s, double *c) {
