@@ -632,6 +632,42 @@ __global__ void fill_power_twiddles(cx<T> *out, long long count, long long mult,
 }
 
 // ------------------------------------------------------------------------------------------
+// Distributed four-step (one transform sharded over P GPUs): between the two local passes every rank
+// holds A[r][c] (r = its block of n2, c = k1) and must hand peer p the columns c in block p.  This kernel
+// multiplies by the inter-pass twiddle W_M^((r0 + r) c) and writes the TRANSPOSE out[c][r], so the slab
+// for peer p (rows p*cols/P .. of `out`) is contiguous and can go straight into the all-to-all.
+template <typename T, bool FWD>
+__global__ void transpose_twiddle(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, int rows, int cols,
+                                  long long r0, const cx<T> *__restrict__ tw_lo, const cx<T> *__restrict__ tw_hi,
+                                  int shift, int mask) {
+    using V = cx<T>;
+    __shared__ V tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+    const int tiles_c = (cols + 31) / 32;
+    const long long tile_id = blockIdx.x;
+    const int c0 = (int)(tile_id % tiles_c) * 32, rr0 = (int)(tile_id / tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int r = rr0 + ty + i, c = c0 + tx;
+        if (r < rows && c < cols) {
+            V v = in[(long long)r * cols + c];
+            if (tw_lo != nullptr) {
+                const unsigned long long p = (unsigned long long)(r0 + r) * (unsigned long long)c;
+                const V w = cmul(__ldg(tw_lo + (unsigned)(p & (unsigned long long)mask)), __ldg(tw_hi + (unsigned)(p >> shift)));
+                v = cmul_tw<FWD>(v, w);
+            }
+            tile[ty + i][tx] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int c = c0 + ty + i, r = rr0 + tx;
+        if (r < rows && c < cols) out[(long long)c * rows + r] = tile[tx][ty + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Frequency-domain pointwise product (mul_op, /root/reference/dsc/include/dsc_ops.h:68-78),
 // b broadcast over rows when b_rows == 0.
 template <typename T>

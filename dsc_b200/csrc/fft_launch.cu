@@ -522,4 +522,43 @@ int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
     return check_launch("cmul_rows");
 }
 
+int dsc_cuda_fill_twiddles(void *out, int64_t count, int64_t mult, int64_t denom, int dtype, void *stream) {
+    if (!out || count <= 0 || denom <= 0) return fail(DSC_CUDA_EINVAL, "dsc_cuda_fill_twiddles: bad argument");
+    const int blocks = (int)((count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024);
+    if (dtype == DSC_CUDA_F32 || dtype == DSC_CUDA_C32)
+        DSC_LAUNCH(fill_power_twiddles<float>, blocks, 256, 0, stream, (float2 *)out, (long long)count, (long long)mult, (long long)denom);
+    else
+        DSC_LAUNCH(fill_power_twiddles<double>, blocks, 256, 0, stream, (double2 *)out, (long long)count, (long long)mult, (long long)denom);
+    return check_launch("fill_power_twiddles");
+}
+
+int dsc_cuda_transpose_twiddle(const void *in, void *out, int64_t rows, int64_t cols, int64_t r0,
+                               const void *tw_lo, const void *tw_hi, int shift, int forward,
+                               int dtype, void *stream) {
+    if (!in || !out || rows <= 0 || cols <= 0 || rows > 0x7fffffff || cols > 0x7fffffff)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_twiddle: bad argument");
+    const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    if (tiles > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_twiddle: too many tiles");
+    const int mask = (1 << shift) - 1;
+    const bool f32 = dtype == DSC_CUDA_F32 || dtype == DSC_CUDA_C32;
+    if (f32 && forward) {
+        auto k = transpose_twiddle<float, true>;
+        DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const float2 *)in, (float2 *)out, (int)rows, (int)cols, (long long)r0,
+                   (const float2 *)tw_lo, (const float2 *)tw_hi, shift, mask);
+    } else if (f32) {
+        auto k = transpose_twiddle<float, false>;
+        DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const float2 *)in, (float2 *)out, (int)rows, (int)cols, (long long)r0,
+                   (const float2 *)tw_lo, (const float2 *)tw_hi, shift, mask);
+    } else if (forward) {
+        auto k = transpose_twiddle<double, true>;
+        DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const double2 *)in, (double2 *)out, (int)rows, (int)cols, (long long)r0,
+                   (const double2 *)tw_lo, (const double2 *)tw_hi, shift, mask);
+    } else {
+        auto k = transpose_twiddle<double, false>;
+        DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const double2 *)in, (double2 *)out, (int)rows, (int)cols, (long long)r0,
+                   (const double2 *)tw_lo, (const double2 *)tw_hi, shift, mask);
+    }
+    return check_launch("transpose_twiddle");
+}
+
 }  // extern "C"

@@ -55,6 +55,9 @@ class CudaApi:
         L.dsc_cuda_irfft.argtypes = L.dsc_cuda_rfft.argtypes
         L.dsc_cuda_cmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                     C.c_int, C.c_void_p]
+        L.dsc_cuda_fill_twiddles.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.dsc_cuda_transpose_twiddle.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
 
     def _check(self, rc: int, what: str) -> None:
         if rc != 0:
@@ -90,3 +93,10 @@ class CudaApi:
     def cmul(self, a_ptr, b_ptr, out_ptr, dtype, rows, cols, b_rows, stream=0):
         self._check(self.lib.dsc_cuda_cmul(a_ptr, b_ptr, out_ptr, dtype, rows, cols, int(b_rows), stream),
                     "dsc_cuda_cmul")
+
+    def fill_twiddles(self, out_ptr, count, mult, denom, dtype, stream=0):
+        self._check(self.lib.dsc_cuda_fill_twiddles(out_ptr, count, mult, denom, dtype, stream), "dsc_cuda_fill_twiddles")
+
+    def transpose_twiddle(self, in_ptr, out_ptr, rows, cols, r0, tw_lo, tw_hi, shift, forward, dtype, stream=0):
+        self._check(self.lib.dsc_cuda_transpose_twiddle(in_ptr, out_ptr, rows, cols, r0, tw_lo, tw_hi, shift,
+                                                        int(forward), dtype, stream), "dsc_cuda_transpose_twiddle")

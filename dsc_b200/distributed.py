@@ -1,0 +1,116 @@
+"""One transform sharded over P GPUs: the four-step decomposition whose transpose is an all-to-all.
+
+N = N1 * N2 points, P ranks (one process per GPU, ``torch.distributed``; NCCL over NVLink on a B200
+box).  Index split  n = n1*N2 + n2,  k = k1 + N1*k2:
+
+    X[k1 + N1 k2] = sum_{n2} W_N2^{n2 k2} [ W_N^{n2 k1} sum_{n1} x[n1 N2 + n2] W_N1^{n1 k1} ]
+
+  layout in  : rank p owns the column block n2 in [p N2/P, (p+1) N2/P), stored n2-major:
+               local[n2_local][n1] = x[n1*N2 + n2]          (so the length-N1 lines are contiguous)
+  step 1     : N2/P local transforms of length N1          (dsc_cuda_fft, sm_100a kernels)
+  step 2     : times W_N^{n2 k1} and transpose to [k1][n2_local] (dsc_cuda_transpose_twiddle): the slab
+               for peer q, k1 in block q, is then contiguous
+  step 3     : all-to-all of the P slabs                    (the ONE exchange; NCCL)
+  step 4     : un-interleave to [k1_local][n2] and N1/P local transforms of length N2
+  layout out : rank p owns k1 in block p: local[k1_local][k2] = X[k1 + N1*k2]   (block-transposed order)
+
+The reference has no counterpart (single process, dsc/src/dsc.cpp:2082-2088 only marks where parallelism
+was intended); parity is checked against its CPU FFT on sizes the oracle can do (tests/test_distributed.py).
+torch supplies device memory, streams and the process group -- plumbing; every transform, twiddle and
+transpose runs in this repo's kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import cuda_api
+
+
+def _ilog2(v: int) -> int:
+    assert v > 0 and v & (v - 1) == 0, "power of two expected"
+    return v.bit_length() - 1
+
+
+class ShardedFFT:
+    def __init__(self, n_total: int, api: cuda_api.CudaApi | None = None, device=None, group=None,
+                 dtype=torch.complex64):
+        self.group = group
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.api = api or cuda_api.CudaApi()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype
+        self.prec = cuda_api.F32 if dtype == torch.complex64 else cuda_api.F64
+        self.code = cuda_api.C32 if dtype == torch.complex64 else cuda_api.C64
+        lg = _ilog2(n_total)
+        self.N = n_total
+        self.N1 = 1 << ((lg + 1) // 2)
+        self.N2 = 1 << (lg // 2)
+        assert self.N1 % self.P == 0 and self.N2 % self.P == 0, "P must divide both factors"
+        self.rows = self.N2 // self.P          # local n2 lines in step 1
+        self.cols = self.N1 // self.P          # local k1 lines in step 4
+        self.plan1, self._mem1 = self._plan(self.N1)
+        self.plan2, self._mem2 = (self.plan1, None) if self.N2 == self.N1 else self._plan(self.N2)
+        # W_N^p through two sqrt(N)-sized tables: p = (p >> shift) << shift | (p & mask)
+        self.shift = (lg + 1) // 2
+        self.tw_lo = torch.empty(1 << self.shift, dtype=dtype, device=self.device)
+        self.tw_hi = torch.empty(1 << (lg - self.shift), dtype=dtype, device=self.device)
+        self.api.fill_twiddles(self.tw_lo.data_ptr(), self.tw_lo.numel(), 1, self.N, self.prec, self._stream())
+        self.api.fill_twiddles(self.tw_hi.data_ptr(), self.tw_hi.numel(), 1 << self.shift, self.N, self.prec, self._stream())
+        wb = max(self.api.work_bytes(self.plan1, self.rows), self.api.work_bytes(self.plan2, self.cols), 256)
+        self.work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+
+    def _plan(self, n):
+        nb = self.api.plan_bytes(n, cuda_api.FFT_COMPLEX, self.prec)
+        assert nb > 0, f"no plan for length {n}"
+        mem = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        return self.api.plan_build(n, cuda_api.FFT_COMPLEX, self.prec, mem.data_ptr(), nb, self._stream()), mem
+
+    # ---- layout helpers (host side, for tests and small inputs) -----------------------------------
+    def scatter_input(self, x_full: torch.Tensor) -> torch.Tensor:
+        """local[n2_local][n1] of this rank from the natural-order vector (every rank passes the same x)."""
+        m = x_full.reshape(self.N1, self.N2)                     # [n1][n2]
+        blk = m[:, self.rank * self.rows:(self.rank + 1) * self.rows]
+        return blk.t().contiguous().to(self.device)
+
+    def gather_output(self, local_out: torch.Tensor) -> torch.Tensor:
+        """Natural-order X on every rank from the block-transposed shards (all_gather + transpose)."""
+        if self.P > 1:
+            parts = [torch.empty_like(local_out) for _ in range(self.P)]
+            dist.all_gather(parts, local_out.contiguous(), group=self.group)
+            full = torch.cat(parts, dim=0)                       # [k1][k2]
+        else:
+            full = local_out
+        return full.t().contiguous().reshape(-1)                 # index k1 + N1*k2
+
+    # ---- the transform -------------------------------------------------------------------------------
+    def forward(self, local_in: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+        """local_in: [N2/P, N1] (n2-major shard).  Returns [N1/P, N2]: X[k1 + N1 k2] for this rank's k1 block."""
+        assert local_in.shape == (self.rows, self.N1) and local_in.dtype == self.dtype and local_in.is_contiguous()
+        api, s = self.api, self._stream()
+        fwd = not inverse
+        a = torch.empty_like(local_in)
+        api.fft(self.plan1, local_in.data_ptr(), self.code, a.data_ptr(), self.rows, self.N1, 1, fwd,
+                self.work.data_ptr(), self.work.numel(), s)
+        # twiddle + transpose: send[k1][n2_local]; rows [q*cols, (q+1)*cols) go to peer q
+        send = torch.empty(self.N1, self.rows, dtype=self.dtype, device=self.device)
+        api.transpose_twiddle(a.data_ptr(), send.data_ptr(), self.rows, self.N1, self.rank * self.rows,
+                              self.tw_lo.data_ptr(), self.tw_hi.data_ptr(), self.shift, fwd, self.code, s)
+        if self.P > 1:
+            recv = torch.empty_like(send)                        # [q][k1_local][n2_local]
+            dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+            b = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
+            b.view(self.cols, self.P, self.rows).copy_(recv.view(self.P, self.cols, self.rows).permute(1, 0, 2))
+        else:
+            b = send                                             # [k1][n2] already
+        out = torch.empty_like(b)
+        api.fft(self.plan2, b.data_ptr(), self.code, out.data_ptr(), self.cols, self.N2, 1, fwd,
+                self.work.data_ptr(), self.work.numel(), s)
+        if inverse:
+            # each local pass scaled by its own 1/length; together that is 1/N
+            pass
+        return out

@@ -97,6 +97,17 @@ int dsc_cuda_irfft(const dsc_cuda_plan *plan, const void *x, void *out,
 int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
                   int64_t rows, int64_t cols, int b_rows, void *stream);
 
+/* ---- building blocks of the multi-GPU four-step (one transform sharded over P GPUs) ----------
+ * out[k] = exp(-2 pi i (k * mult mod denom) / denom), k < count: the two sqrt(M)-sized tables
+ * lo[p] = W_M^p (mult 1) and hi[q] = W_M^(q << shift) (mult 1 << shift) give W_M^p for any p < M. */
+int dsc_cuda_fill_twiddles(void *out, int64_t count, int64_t mult, int64_t denom, int dtype, void *stream);
+
+/* out[c][r] = in[r][c] * W_M^((r0 + r) * c) (conjugated when !forward); in is rows x cols row-major.
+ * tw_lo == NULL: plain transpose.  The rows of `out` that belong to peer p are contiguous. */
+int dsc_cuda_transpose_twiddle(const void *in, void *out, int64_t rows, int64_t cols, int64_t r0,
+                               const void *tw_lo, const void *tw_hi, int shift, int forward,
+                               int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
