@@ -99,7 +99,7 @@ FusedEntry make_fused() {
     FusedEntry e;
     e.fn = four_step_fused<T, LG_N1, LG_N2, THREADS, FWD>;
     e.lg_n1 = LG_N1; e.lg_n2 = LG_N2; e.threads = THREADS; e.lpb_a = LPB_A; e.lpb_b = LPB_B;
-    e.smem = (SM_A > SM_B ? SM_A : SM_B) * (int)sizeof(cx<T>);
+    e.smem = ((SM_A + LPB_A * (1 << LG_E1)) > SM_B ? (SM_A + LPB_A * (1 << LG_E1)) : SM_B) * (int)sizeof(cx<T>);   // + W^(q TT c) tables
     e.configured = false;
     return e;
 }

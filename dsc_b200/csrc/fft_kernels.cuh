@@ -176,7 +176,21 @@ template <typename T> DSC_DEV cx<T> four_step_twiddle(const FftArgs &a, const un
 
 // Streaming accesses for the payload: each element is touched exactly once, so it should not
 // displace the twiddle tables from L1 / linger in L2 (ld.global.cs / st.global.cs).
-template <typename V> DSC_DEV V ld_stream(const V *p) { return __ldcs(p); }
+#if defined(DSC_EMUL)
+template <typename V> DSC_DEV V ld_stream(const V *p) { return *p; }
+#else
+// no L1 allocation at all: the payload must not evict the twiddle tables, which are the only data with reuse
+DSC_DEV float2 ld_stream(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+DSC_DEV double2 ld_stream(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+#endif
 template <typename V> DSC_DEV void st_stream(V *p, const V v) { __stcs(p, v); }
 
 // Un-mix / mix step of the packed real transform for one bin pair (k, N-k).
@@ -251,6 +265,12 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     // read iff offset < lim; "no limit" (dense lines) is encoded as a huge lim by the host
     const long long lim = active ? a.in_limit - in * a.gi.lstride : 0;
     const V zero = mk<T>((T)0, (T)0);
+    // PASS_A: per-line table W_M^(q * TT * c), c < E, behind the line buffers (visible after the tile-load barrier)
+    V *tw_c = sm_all + LPB * LINE;
+    if constexpr (MODE == MODE_PASS_A) {
+        if (a.four_shift)
+            for (int c = t; c < E; c += TT) tw_c[l * E + c] = four_step_twiddle<T>(a, (unsigned)in * (unsigned)(TT * c));
+    }
     // cooperative tile copies (TILED): lane = line within the tile, then position; each thread moves E
     // elements at positions p0 + c*TT of line lt.  The fused launch guarantees whole tiles inside one row.
     const int lt = tid % LPB, p0 = tid / LPB;
@@ -268,7 +288,12 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
         // every line of the block exists and is dense: a.x / a.out are (lines, N) row-major
         const V *__restrict__ xp = (const V *)a.x + line * N + t;
 #pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = ld_stream(xp + c * TT);
+        for (int c = 0; c < E; ++c) {
+            // with fewer than 32 threads per line a warp's accesses are only coalesced ACROSS the c loop:
+            // let L1 merge them; full warps per line stream past L1
+            if constexpr (TT >= 32) v[c] = ld_stream(xp + c * TT);
+            else v[c] = __ldcs(xp + c * TT);
+        }
     } else if constexpr (MODE == MODE_PASS_A) {
         // strided source tile -> shared memory (adjacent lanes = adjacent lines = contiguous bytes)
         const long long row_in = a.ring_in ? tile_o % a.ring_in : tile_o;
@@ -396,11 +421,15 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
 #pragma unroll
         for (int c = 0; c < E; ++c) st_stream(op + c * TT, v[c]);
     } else if constexpr (TILED) {
-        if (MODE == MODE_PASS_A && a.four_shift) {   // times W_M^(n2 * k1), n2 = this line's column
-            const unsigned q = (unsigned)in;
+        if (MODE == MODE_PASS_A && a.four_shift) {
+            // times W_M^(q k1), q = this line's column n2, k1 = t + c*TT:  W^(q t) * W^(q TT c).
+            // The first factor is one (two-table) lookup per thread; the second depends only on (line, c)
+            // and was put in shared memory by the line's first E threads at kernel start -- 16 broadcast
+            // LDS instead of 32 scattered global gathers per thread.
+            const V w0 = four_step_twiddle<T>(a, (unsigned)in * (unsigned)t);
+            const V *tc = tw_c + l * E;
 #pragma unroll
-            for (int c = 0; c < E; ++c)
-                v[c] = cmul_tw<FWD>(v[c], four_step_twiddle<T>(a, q * (unsigned)(t + c * TT)));
+            for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], c == 0 ? w0 : cmul(w0, tc[c]));
         }
         // registers -> shared memory (own line), then the block stores the tile with adjacent lanes on
         // adjacent lines: contiguous LPB*sizeof(V) bytes per position
