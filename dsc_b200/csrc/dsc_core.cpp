@@ -447,20 +447,11 @@ void launch_chunk(dsc_ctx *ctx, const xform_job &j, const byte *dx, byte *dout, 
         case XF_IRFFT:
             rc = dsc_cuda_irfft(&j.plan->cu, src, dst, rows, j.x_n, j.inner, work, work_bytes, s);
             break;
-        case XF_FILTER: {
-            // rfft -> spectrum product -> irfft, all on the device; the spectrum lives in `work`
-            const usize es = j.plan->cu.dtype == DSC_CUDA_F32 ? sizeof(c32) : sizeof(c64);
-            const i64 bins = (i64) j.plan->cu.n + 1;
-            const usize spec_bytes = DSC_ALIGN((usize) rows * (usize) bins * es, DEV_GRANULE);
-            DSC_ASSERT(work_bytes > spec_bytes);
-            byte *spec = (byte *) work;
-            byte *rest = spec + spec_bytes;
-            rc = dsc_cuda_rfft(&j.plan->cu, src, spec, rows, j.x_n, 1, rest, work_bytes - spec_bytes, s);
-            if (rc == 0) rc = dsc_cuda_cmul(spec, dsc_dev_ptr(ctx, j.spectrum->buffer), spec,
-                                            j.plan->cu.dtype == DSC_CUDA_F32 ? DSC_CUDA_C32 : DSC_CUDA_C64, rows, bins, 0, s);
-            if (rc == 0) rc = dsc_cuda_irfft(&j.plan->cu, spec, dst, rows, (int) bins, 1, rest, work_bytes - spec_bytes, s);
+        case XF_FILTER:
+            // rfft -> spectrum product -> irfft without the spectrum ever leaving the device (one kernel for
+            // orders that fit shared memory)
+            rc = dsc_cuda_filter(&j.plan->cu, src, dsc_dev_ptr(ctx, j.spectrum->buffer), dst, rows, j.x_n, work, work_bytes, s);
             break;
-        }
     }
     if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
 }
@@ -508,19 +499,12 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
     usize work_bytes = 0;
     void *work = nullptr;
     {
-        usize need = dsc_cuda_work_bytes(&j.plan->cu, DSC_MIN(rows_per_chunk, j.outer) * j.inner);
-        if (j.kind == XF_FILTER) {
-            const usize es = j.plan->cu.dtype == DSC_CUDA_F32 ? sizeof(c32) : sizeof(c64);
-            need += DSC_ALIGN((usize) DSC_MIN(rows_per_chunk, j.outer) * ((usize) j.plan->cu.n + 1) * es, DEV_GRANULE) + DEV_GRANULE;
-        }
+        const i64 lines = DSC_MIN(rows_per_chunk, j.outer) * j.inner;
+        const usize need = j.kind == XF_FILTER ? dsc_cuda_filter_work_bytes(&j.plan->cu, lines)
+                                               : dsc_cuda_work_bytes(&j.plan->cu, lines);
         if (need > 0) {
-            work_bytes = DSC_MIN(need, ctx->dev_scratch.capacity);
-            if (j.kind == XF_FILTER && work_bytes < need) {
-                // the spectrum must fit: shrink the chunk instead
-                const usize per_row = need / (usize) DSC_MIN(rows_per_chunk, j.outer);
-                rows_per_chunk = DSC_MAX((i64) (work_bytes / DSC_MAX(per_row, (usize) 1)) - 1, (i64) 0);
-                if (rows_per_chunk < 1) DSC_LOG_FATAL("scratch memory too small for one line of the filter pipeline");
-            }
+            // less than `need` still works (the launch layer chunks); one line must fit
+            work_bytes = DSC_MIN(need, ctx->dev_scratch.capacity) / DEV_GRANULE * DEV_GRANULE;
             const usize off = ctx->dev_scratch.alloc(work_bytes, DEV_GRANULE);
             DSC_ASSERT(off != (usize) -1);
             work = ctx->dev_base + (ctx->dev_size - ctx->dev_scratch_size) + off;

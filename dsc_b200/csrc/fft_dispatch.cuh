@@ -74,6 +74,7 @@ DSC_DECLARE_TABLE(double, true, MODE_C2C, false)  DSC_DECLARE_TABLE(double, true
 DSC_DECLARE_TABLE(double, false, MODE_C2C, false) DSC_DECLARE_TABLE(double, false, MODE_C2C, true)
 DSC_DECLARE_TABLE(float, true, MODE_R2C, false)   DSC_DECLARE_TABLE(float, false, MODE_C2R, false)
 DSC_DECLARE_TABLE(double, true, MODE_R2C, false)  DSC_DECLARE_TABLE(double, false, MODE_C2R, false)
+DSC_DECLARE_TABLE(float, true, MODE_FILTER, false) DSC_DECLARE_TABLE(double, true, MODE_FILTER, false)
 DSC_DECLARE_TABLE(float, true, MODE_FAST, false)  DSC_DECLARE_TABLE(float, false, MODE_FAST, false)
 DSC_DECLARE_TABLE(double, true, MODE_FAST, false) DSC_DECLARE_TABLE(double, false, MODE_FAST, false)
 #undef DSC_DECLARE_TABLE

@@ -35,6 +35,7 @@ enum Mode : int {
                     // one base pointer per thread, immediate offsets, streaming cache hints
     MODE_PASS_A = 4,  // MODE_C2C as the first pass of the fused four-step kernel (payload in, L2 out)
     MODE_PASS_B = 5,  // MODE_C2C/IN_ROWS as its second pass (L2 in, payload out)
+    MODE_FILTER = 6,  // rfft -> times a spectrum -> irfft in ONE kernel: the spectrum never leaves shared memory
 };
 
 // how MODE_C2C reads its input
@@ -72,6 +73,7 @@ struct FftArgs {
     int strided;          // thread mapping: 1 = adjacent lines on adjacent lanes
     int inner_shift;      // log2(inner) when inner is a power of two, else -1
     int no_limit;         // every line exists and is read in full: skip the pad/crop predicates
+    const void *filt;     // MODE_FILTER: N+1 bins multiplied into every line's spectrum
     long long ring_in;    // input / output row index taken modulo this (0 = off): ring of work rows
     long long ring_out;
     double scale;         // applied to the outputs when do_scale (1/N of the inverse)
@@ -204,6 +206,28 @@ DSC_DEV void real_pair(const cx<T> a, const cx<T> b, const cx<T> w_fwd, cx<T> &r
     const T wr = w_fwd.x, wi = FWD ? w_fwd.y : -w_fwd.y;
     ra = mk<T>(h1r + wr * h2r - wi * h2i,  h1i + wr * h2i + wi * h2r);
     rb = mk<T>(h1r - wr * h2r + wi * h2i, -h1i + wr * h2i + wi * h2r);
+}
+
+// rfft un-mix, spectrum product, irfft mix for one bin pair (k, N-k) in a single step:
+// (Z[k], Z[N-k]) -> (X[k], X[N-k]) -> times (B[k], B[N-k]) -> packed (z'[k], z'[N-k]).
+template <typename T>
+DSC_DEV void filter_pair(const cx<T> za, const cx<T> zb, const cx<T> w_fwd, const cx<T> ba, const cx<T> bb,
+                         cx<T> &ra, cx<T> &rb) {
+    cx<T> xa, xb;
+    real_pair<true, T>(za, zb, w_fwd, xa, xb);
+    real_pair<false, T>(cmul(xa, ba), cmul(xb, bb), w_fwd, ra, rb);
+}
+// the self-paired bins: DC + Nyquist (from Z[0]) and, for N >= 2, bin N/2
+template <typename T>
+DSC_DEV cx<T> filter_dc(const cx<T> z0, const cx<T> b0, const cx<T> bn) {
+    // X[0] = (z0.x + z0.y, 0), X[N] = (z0.x - z0.y, 0); only the REAL parts of the products enter the inverse
+    const T y0 = (z0.x + z0.y) * b0.x, yn = (z0.x - z0.y) * bn.x;
+    return mk<T>((T)0.5 * (y0 + yn), (T)0.5 * (y0 - yn));
+}
+template <typename T>
+DSC_DEV cx<T> filter_mid(const cx<T> zh, const cx<T> bh) {
+    const cx<T> y = cmul(mk<T>(zh.x, -zh.y), bh);     // X[N/2] = conj(Z[N/2])
+    return mk<T>(y.x, -y.y);                          // z'[N/2] = conj(Y[N/2])
 }
 
 // Payload access with a compile-time cache policy.
@@ -357,7 +381,7 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
         __syncthreads();
-    } else if (MODE == MODE_R2C || a.in_kind == IN_PAIRS) {
+    } else if (MODE == MODE_R2C || MODE == MODE_FILTER || a.in_kind == IN_PAIRS) {
         // 2N reals seen as N complex: z[j] = (x[..2j], x[..2j+1]); gi is in REAL elements
         const T *__restrict__ xr = (const T *)a.x + ibase;
 #pragma unroll
@@ -407,7 +431,38 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     }
 
     // ---------------------------------------------------------------- transform
-    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, t, a, ls);
+    if constexpr (MODE == MODE_FILTER) {
+        // forward packed transform, then per bin pair un-mix * spectrum * mix in shared memory, then the
+        // inverse packed transform: the same registers and the same line buffer all the way
+        Stage<T, LG_N, LG_E, true, 0>::run(v, sm, t, a, ls);
+        __syncthreads();
+        const int ptf = Sc::pad(t);
+#pragma unroll
+        for (int c = 0; c < E; ++c) sm[Sc::pad_read(t, ptf, c)] = v[c];
+        __syncthreads();
+        const V *__restrict__ twr = (const V *)a.tw_real;
+        const V *__restrict__ bf = (const V *)a.filt;
+#pragma unroll
+        for (int c = 0; c < PAIRS; ++c) {
+            const int k = t + c * TT;
+            if (c == 0 && k == 0) {
+                sm[Sc::pad(0)] = filter_dc<T>(sm[Sc::pad(0)], __ldg(bf), __ldg(bf + N));
+                if (N >= 2) sm[Sc::pad(N / 2)] = filter_mid<T>(sm[Sc::pad(N / 2)], __ldg(bf + N / 2));
+            } else if (k < N / 2) {
+                V ra, rb;
+                filter_pair<T>(sm[Sc::pad(k)], sm[Sc::pad(N - k)], __ldg(twr + k), __ldg(bf + k), __ldg(bf + (N - k)), ra, rb);
+                sm[Sc::pad(k)] = ra;
+                sm[Sc::pad(N - k)] = rb;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, ptf, c)];
+        __syncthreads();
+        Stage<T, LG_N, LG_E, false, 0>::run(v, sm, t, a, ls);
+    } else {
+        Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, t, a, ls);
+    }
 
     if (a.do_scale) {
         const T s = (T)a.scale;
@@ -455,7 +510,7 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
 #pragma unroll
             for (int c = 0; c < E; ++c) st_pol<POL_OUT>(oc + c * ostep, v[c]);
         }
-    } else if constexpr (MODE == MODE_C2R) {
+    } else if constexpr (MODE == MODE_C2R || MODE == MODE_FILTER) {
         // N complex = 2N reals; go is in REAL elements
         if (active) {
             T *__restrict__ orl = (T *)a.out + obase + ooff0;
@@ -626,6 +681,33 @@ __global__ void real_mix_rows(const cx<T> *__restrict__ x, cx<T> *__restrict__ z
                 zr[k] = za;
                 zr[n - k] = zb;
             }
+        }
+    }
+}
+
+// Filter pipeline for orders beyond one shared-memory pass: between the forward and the inverse four-step
+// transforms, ONE elementwise kernel turns packed Z rows into packed z' rows in place (un-mix, spectrum
+// product, mix per bin pair) -- instead of un-mix, product and mix as three sweeps.
+template <typename T>
+__global__ void filter_pairs_rows(cx<T> *__restrict__ z, const cx<T> *__restrict__ spectrum, long long rows, int n,
+                                  const cx<T> *__restrict__ tw_lo, const cx<T> *__restrict__ tw_hi, int shift, int mask) {
+    using V = cx<T>;
+    const int half = n / 2;
+    const long long total = rows * (long long)half;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / half;
+        const int k = (int)(i - row * half);
+        V *zr = z + row * (long long)n;
+        if (k == 0) {
+            zr[0] = filter_dc<T>(zr[0], __ldg(spectrum), __ldg(spectrum + n));
+            zr[half] = filter_mid<T>(zr[half], __ldg(spectrum + half));
+        } else {
+            const V w = cmul(__ldg(tw_lo + (k & mask)), __ldg(tw_hi + (k >> shift)));
+            V ra, rb;
+            filter_pair<T>(zr[k], zr[n - k], w, __ldg(spectrum + k), __ldg(spectrum + (n - k)), ra, rb);
+            zr[k] = ra;
+            zr[n - k] = rb;
         }
     }
 }

@@ -417,6 +417,64 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
     return 0;
 }
 
+template <typename T>
+int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void *out, long long outer, int x_n,
+               void *work, size_t work_bytes, void *stream) {
+    using V = cx<T>;
+    const long long n = p->n;
+    const long long take = x_n < 2 * n ? x_n : 2 * n;
+    if (p->lg_n2 == 0) {
+        FftArgs a{};
+        a.x = x; a.out = out;
+        a.lines = outer;
+        a.inner = 1;
+        a.gi = LineGeom{(long long)x_n, 1, 2};                   // REAL elements
+        a.gi_pstride = 1;
+        a.go = LineGeom{2 * n, 1, 2};                            // REAL elements
+        a.go_pstride = 1;
+        a.in_limit = take;
+        set_stage_tables<T>(a, p->tw1);
+        a.tw_real = p->tw_real;
+        a.filt = spectrum;
+        a.do_scale = 1; a.scale = 1.0 / (double)n;
+        return launch_lines(get_table<T, true, MODE_FILTER, false>(), p->lg_n, a, stream);
+    }
+    // rows in flight: packed spectrum rows of the chunk + four-step work
+    const size_t row_bytes = (size_t)n * sizeof(V);
+    if (!work || work_bytes < 2 * row_bytes + 4096) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
+    long long chunk = (long long)((work_bytes / 2) / row_bytes);
+    if (chunk > outer) chunk = outer;
+    V *z = (V *)work;
+    char *fs_work = (char *)work + align_up((size_t)chunk * row_bytes, 256);
+    const size_t fs_bytes = work_bytes - (size_t)(fs_work - (char *)work);
+    for (long long r0 = 0; r0 < outer; r0 += chunk) {
+        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
+        FftArgs a{};
+        a.x = (const T *)x + (size_t)r0 * x_n;
+        a.gi = LineGeom{(long long)x_n, 2, 2LL << p->lg_n2};     // REAL elements
+        a.gi_pstride = 1;
+        a.in_limit = take;
+        a.in_kind = IN_PAIRS;
+        int rc = four_step<T, true>(p, a, rows, fs_work, fs_bytes, z, n, false, stream);
+        if (rc) return rc;
+        const long long items = rows * (n / 2);
+        const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+        auto pk = filter_pairs_rows<T>;
+        DSC_LAUNCH(pk, blocks, 256, 0, stream, z, (const V *)spectrum, rows, (int)n,
+                   (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift, (1 << p->real_shift) - 1);
+        rc = check_launch("filter_pairs_rows");
+        if (rc) return rc;
+        FftArgs b{};
+        b.x = z;
+        b.gi = LineGeom{n, 1, 1LL << p->lg_n2};
+        b.in_limit = n;
+        b.in_kind = IN_COMPLEX;
+        rc = four_step<T, false>(p, b, rows, fs_work, fs_bytes, (V *)out + (size_t)r0 * n, n, true, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 bool plan_ok(const dsc_cuda_plan *p) {
     return p && p->n >= 1 && (p->dtype == DSC_CUDA_F32 || p->dtype == DSC_CUDA_F64);
 }
@@ -504,6 +562,24 @@ int dsc_cuda_irfft(const dsc_cuda_plan *plan, const void *x, void *out,
         return fail(DSC_CUDA_EINVAL, "dsc_cuda_irfft: bad argument");
     return plan->dtype == DSC_CUDA_F32 ? run_irfft<float>(plan, x, out, outer, x_n, inner, work, work_bytes, stream)
                                        : run_irfft<double>(plan, x, out, outer, x_n, inner, work, work_bytes, stream);
+}
+
+size_t dsc_cuda_filter_work_bytes(const dsc_cuda_plan *plan, int64_t lines) {
+    if (!plan_ok(plan) || plan->lg_n2 == 0 || lines <= 0) return 0;
+    // packed spectrum rows of the lines in flight (about as many as keep the GPU busy) + four-step work
+    const size_t es = plan->dtype == DSC_CUDA_F64 ? sizeof(double2) : sizeof(float2);
+    const size_t row = (size_t)plan->n * es;
+    size_t rows = (256u << 20) / row > 8 ? (256u << 20) / row : 8;
+    if (rows > (size_t)lines) rows = (size_t)lines;
+    return 2 * (rows * row + dsc_cuda_work_bytes(plan, (int64_t)rows)) + 4096;
+}
+
+int dsc_cuda_filter(const dsc_cuda_plan *plan, const void *x, const void *spectrum, void *out,
+                    int64_t outer, int x_n, void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || plan->fft_type != DSC_CUDA_FFT_REAL || !x || !spectrum || !out || x_n < 1 || outer < 0)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_filter: bad argument");
+    return plan->dtype == DSC_CUDA_F32 ? run_filter<float>(plan, x, spectrum, out, outer, x_n, work, work_bytes, stream)
+                                       : run_filter<double>(plan, x, spectrum, out, outer, x_n, work, work_bytes, stream);
 }
 
 int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,

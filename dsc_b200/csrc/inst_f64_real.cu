@@ -4,4 +4,5 @@
 namespace dscfft {
 DSC_DEFINE_TABLE(double, true, MODE_R2C, false)
 DSC_DEFINE_TABLE(double, false, MODE_C2R, false)
+DSC_DEFINE_TABLE(double, true, MODE_FILTER, false)
 }

@@ -55,6 +55,9 @@ class CudaApi:
         L.dsc_cuda_irfft.argtypes = L.dsc_cuda_rfft.argtypes
         L.dsc_cuda_cmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                     C.c_int, C.c_void_p]
+        L.dsc_cuda_filter_work_bytes.restype = C.c_size_t
+        L.dsc_cuda_filter_work_bytes.argtypes = [pp, C.c_int64]
+        L.dsc_cuda_filter.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_fill_twiddles.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.dsc_cuda_transpose_twiddle.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -100,3 +103,10 @@ class CudaApi:
     def transpose_twiddle(self, in_ptr, out_ptr, rows, cols, r0, tw_lo, tw_hi, shift, forward, dtype, stream=0):
         self._check(self.lib.dsc_cuda_transpose_twiddle(in_ptr, out_ptr, rows, cols, r0, tw_lo, tw_hi, shift,
                                                         int(forward), dtype, stream), "dsc_cuda_transpose_twiddle")
+
+    def filter_work_bytes(self, plan, lines):
+        return self.lib.dsc_cuda_filter_work_bytes(C.byref(plan), lines)
+
+    def filter(self, plan, x_ptr, spectrum_ptr, out_ptr, outer, x_n, work_ptr=0, work_bytes=0, stream=0):
+        self._check(self.lib.dsc_cuda_filter(C.byref(plan), x_ptr, spectrum_ptr, out_ptr, outer, x_n,
+                                             work_ptr, work_bytes, stream), "dsc_cuda_filter")

@@ -92,6 +92,15 @@ int dsc_cuda_irfft(const dsc_cuda_plan *plan, const void *x, void *out,
                    int64_t outer, int x_n, int64_t inner,
                    void *work, size_t work_bytes, void *stream);
 
+/* Fused filter pipeline (README.md:118-134): out = irfft(rfft(x, 2n) * spectrum) per line of a contiguous
+ * (outer, x_n) real tensor; `spectrum` holds n+1 complex bins and is broadcast over lines; out is
+ * (outer, 2n) real.  Orders that fit one shared-memory pass run as ONE kernel (the line's spectrum never
+ * leaves shared memory); larger orders as fused four-step forward, one bin-pair kernel, fused four-step
+ * inverse.  work: dsc_cuda_filter_work_bytes(plan, lines). */
+size_t dsc_cuda_filter_work_bytes(const dsc_cuda_plan *plan, int64_t lines);
+int dsc_cuda_filter(const dsc_cuda_plan *plan, const void *x, const void *spectrum, void *out,
+                    int64_t outer, int x_n, void *work, size_t work_bytes, void *stream);
+
 /* out = a * b elementwise on complex rows; b has `cols` elements (b_rows == 0, broadcast)
  * or rows*cols (b_rows != 0). */
 int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,

@@ -162,3 +162,20 @@ class DevFFT:
         self.api.cmul(self.mem.ptr(da), self.mem.ptr(db), self.mem.ptr(dout), _CODE[a.dtype], rows, cols,
                       b.size == a.size and rows > 1)
         return self.mem.download(dout)
+
+    def filter(self, x, B, n=-1):
+        """irfft(rfft(x, n) * B) along the last axis through dsc_cuda_filter."""
+        x = np.ascontiguousarray(x)
+        x2 = x.reshape(-1, x.shape[-1])
+        order, bins = port.rfft_len(x2.shape[1], n)
+        prec = 0 if x.dtype == np.float32 else 1
+        plan = self.plan(order, cuda_api.FFT_REAL, prec)
+        B = np.ascontiguousarray(B, dtype=_CPLX[x.dtype])
+        assert B.size == bins
+        dx, dB = self.mem.upload(x2), self.mem.upload(B)
+        dout = self.mem.empty((x2.shape[0], 2 * order), x.dtype)
+        nbytes = self.api.filter_work_bytes(plan, x2.shape[0] if self.work_lines is None else min(x2.shape[0], self.work_lines))
+        w = self.mem.alloc(nbytes) if nbytes else None
+        self.api.filter(plan, self.mem.ptr(dx), self.mem.ptr(dB), self.mem.ptr(dout), x2.shape[0], x2.shape[1],
+                        self.mem.ptr(w) if nbytes else 0, nbytes)
+        return self.mem.download(dout).reshape(x.shape[:-1] + (2 * order,))

@@ -175,6 +175,22 @@ def test_two_pass_real(dev, dtype, lg):
     assert rel_l2(dev.irfft(Xs, n=want.shape[1]), port.irfft(Xs, n=want.shape[1])) < TIGHT[dtype]
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_fused_filter(dev, dtype):
+    """irfft(rfft(x, n) * B) as one kernel (single pass) and as four-step + bin-pair kernel (large order)."""
+    rng = np.random.default_rng(21)
+    for rows, xn, n in [(3, 100, 256), (1, 8192, 16384), (5, 2, 2), (2, 64, 4), (2, 3000, 1 << 16)]:
+        if dtype == "float64" and n > 1 << 15:
+            n = 1 << 15
+        x = randn(rng, (rows, xn), dtype)
+        b = randn(rng, (min(xn, 37),), dtype)
+        B = port.rfft(b, n)
+        want = port.irfft(port.cmul(port.rfft(x, n), B))
+        got = dev.filter(x, B, n)
+        assert got.shape == want.shape and got.dtype == want.dtype
+        assert rel_l2(got, want) < TIGHT[dtype] * 3, (rows, xn, n, rel_l2(got, want))
+
+
 def test_cmul(dev):
     rng = np.random.default_rng(1)
     for dt in ("complex64", "complex128"):
