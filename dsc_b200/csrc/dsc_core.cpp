@@ -395,15 +395,36 @@ dsc_fft_plan *dsc_plan_fft(dsc_ctx *ctx, const int n, const dsc_fft_type fft_typ
         ctx->fft_plans[slot] = nullptr;
     }
 
-    const usize bytes = dsc_cuda_plan_bytes(fft_n, fft_type, prec);
-    if (bytes == 0) DSC_LOG_FATAL("FFT length %d is outside the supported range", fft_n);
+    usize bytes = dsc_cuda_plan_bytes(fft_n, fft_type, prec);
+    int lg = 0;
+    while ((1 << lg) < fft_n) ++lg;
+    const int huge_lg = (int) env_size("DSC_HUGE_LG", 0);          // testing knob: compose above 2^DSC_HUGE_LG
+    const bool huge = bytes == 0 || (huge_lg > 0 && lg > huge_lg && fft_type == COMPLEX);
+    const usize es = prec == DSC_CUDA_F32 ? sizeof(c32) : sizeof(c64);
+    if (huge) {
+        if (fft_type != COMPLEX) DSC_LOG_FATAL("real transforms of order %d are outside the supported range", fft_n);
+        bytes = (((usize) 1 << ((lg + 1) / 2)) + ((usize) 1 << (lg - (lg + 1) / 2))) * es + 2 * DEV_GRANULE;
+    }
     const int node = ctx->dev_alloc.alloc(bytes);
     if (node < 0) DSC_LOG_FATAL("device arena exhausted while planning an FFT of length %d (%.1fMB of tables)", fft_n, DSC_B_TO_MB(bytes));
+    byte *mem = ctx->dev_base + ctx->dev_alloc.nodes[node].off;
 
     plan = &ctx->plan_storage[slot];
-    const int rc = dsc_cuda_plan_build(&plan->cu, fft_n, fft_type, prec, ctx->dev_base + ctx->dev_alloc.nodes[node].off,
-                                       bytes, dscdev::stream(0));
-    if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    memset(plan, 0, sizeof(*plan));
+    if (huge) {
+        plan->cu.n = fft_n; plan->cu.lg_n = lg; plan->cu.fft_type = fft_type; plan->cu.dtype = prec;
+        plan->huge = true;
+        plan->lg_h1 = (lg + 1) / 2; plan->lg_h2 = lg / 2;
+        plan->h_shift = (lg + 1) / 2;
+        plan->h_lo = mem;
+        plan->h_hi = mem + DSC_ALIGN(((usize) 1 << plan->h_shift) * es, DEV_GRANULE);
+        int rc = dsc_cuda_fill_twiddles(plan->h_lo, (i64) 1 << plan->h_shift, 1, fft_n, prec, dscdev::stream(0));
+        if (rc == 0) rc = dsc_cuda_fill_twiddles(plan->h_hi, (i64) 1 << (lg - plan->h_shift), (i64) 1 << plan->h_shift, fft_n, prec, dscdev::stream(0));
+        if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    } else {
+        const int rc = dsc_cuda_plan_build(&plan->cu, fft_n, fft_type, prec, mem, bytes, dscdev::stream(0));
+        if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    }
     plan->last_used = 0;
     plan->dev_node = node;
     ctx->fft_plans[slot] = plan;
@@ -425,7 +446,53 @@ struct xform_job {
     const dsc_tensor *spectrum;     // XF_FILTER: B = rfft(b), broadcast over lines
     i64 outer, inner;
     int x_n, out_n;
+    // composed paths (see launch_chunk): two device temporaries and, for huge plans, the sub-plans
+    byte *tmp_a, *tmp_b;
+    const dsc_fft_plan *sub1, *sub2;
 };
+
+#define CUDA_RC(call) do { const int rc_ = (call); if (rc_ != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error()); } while (0)
+
+bool is_composed(const xform_job &j) noexcept {
+    return j.plan->huge || (j.plan->cu.lg_n2 != 0 && j.inner > 1);
+}
+
+int one_transform(const xform_job &j, const dsc_cuda_plan *plan, const void *src, const int src_dtype, void *dst,
+                  const i64 lines, const int x_n, void *work, const usize work_bytes, void *s) noexcept {
+    switch (j.kind) {
+        case XF_FFT:  return dsc_cuda_fft(plan, src, src_dtype, dst, lines, x_n, 1, 1, work, work_bytes, s);
+        case XF_IFFT: return dsc_cuda_fft(plan, src, src_dtype, dst, lines, x_n, 1, 0, work, work_bytes, s);
+        case XF_RFFT: return dsc_cuda_rfft(plan, src, dst, lines, x_n, 1, work, work_bytes, s);
+        case XF_IRFFT: return dsc_cuda_irfft(plan, src, dst, lines, x_n, 1, work, work_bytes, s);
+        default: return -1;
+    }
+}
+
+// A transform of more than one shared-memory pass along a NON-last axis: per outer index, transpose the
+// (n, inner) slab so the lines become contiguous, transform, transpose back.
+void strided_large_slab(const xform_job &j, const byte *src, byte *dst, void *work, const usize work_bytes, void *s) noexcept {
+    const int in_es = (int) DSC_DTYPE_SIZE[j.x->dtype], out_es = (int) DSC_DTYPE_SIZE[j.out->dtype];
+    CUDA_RC(dsc_cuda_transpose(src, j.tmp_a, j.x_n, j.inner, in_es, s));
+    CUDA_RC(one_transform(j, &j.plan->cu, j.tmp_a, j.x->dtype, j.tmp_b, j.inner, j.x_n, work, work_bytes, s));
+    CUDA_RC(dsc_cuda_transpose(j.tmp_b, dst, j.inner, j.out_n, out_es, s));
+}
+
+// One line of a huge plan n = h1 * h2 (index n = a*h2 + b): transpose (+cast, +zero pad) to [b][a], h2
+// transforms of length h1, twiddle W_n^(b k1) + transpose to [k1][b], h1 transforms of length h2,
+// transpose to natural order X[k1 + h1 k2].  Each sub-transform may itself be a fused four-step launch.
+void huge_line(const xform_job &j, const byte *src, byte *dst, void *work, const usize work_bytes, void *s) noexcept {
+    const dsc_fft_plan *p = j.plan;
+    const i64 h1 = (i64) 1 << p->lg_h1, h2 = (i64) 1 << p->lg_h2;
+    const bool fwd = j.kind == XF_FFT;
+    const int cplx = p->cu.dtype == DSC_CUDA_F32 ? DSC_CUDA_C32 : DSC_CUDA_C64;
+    const int es = p->cu.dtype == DSC_CUDA_F32 ? (int) sizeof(c32) : (int) sizeof(c64);
+    const i64 take = DSC_MIN((i64) j.x_n, (i64) p->cu.n);
+    CUDA_RC(dsc_cuda_transpose_cast(src, j.x->dtype, j.tmp_a, h1, h2, take, s));
+    CUDA_RC(dsc_cuda_fft(&j.sub1->cu, j.tmp_a, cplx, j.tmp_b, h2, (int) h1, 1, fwd, work, work_bytes, s));
+    CUDA_RC(dsc_cuda_transpose_twiddle(j.tmp_b, j.tmp_a, h2, h1, 0, p->h_lo, p->h_hi, p->h_shift, fwd, cplx, s));
+    CUDA_RC(dsc_cuda_fft(&j.sub2->cu, j.tmp_a, cplx, j.tmp_b, h1, (int) h2, 1, fwd, work, work_bytes, s));
+    CUDA_RC(dsc_cuda_transpose(j.tmp_b, dst, h1, h2, es, s));
+}
 
 // One chunk of lines [r0, r0 + rows) on the compute stream.
 void launch_chunk(dsc_ctx *ctx, const xform_job &j, const byte *dx, byte *dout, const i64 r0, const i64 rows,
@@ -435,6 +502,15 @@ void launch_chunk(dsc_ctx *ctx, const xform_job &j, const byte *dx, byte *dout, 
     const void *src = dx + (usize) r0 * in_row;
     void *dst = dout + (usize) r0 * out_row;
     void *s = dscdev::stream(0);
+    if (is_composed(j)) {
+        for (i64 r = 0; r < rows; ++r) {
+            const byte *rs = (const byte *) src + (usize) r * in_row;
+            byte *rd = (byte *) dst + (usize) r * out_row;
+            if (j.plan->huge) huge_line(j, rs, rd, work, work_bytes, s);
+            else strided_large_slab(j, rs, rd, work, work_bytes, s);
+        }
+        return;
+    }
     int rc = 0;
     switch (j.kind) {
         case XF_FFT:
@@ -511,6 +587,39 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
         }
     }
 
+    // composed paths: two device temporaries from the arena for the duration of the op
+    int tmp_nodes[2] = {-1, -1};
+    xform_job jj = j;
+    if (is_composed(j)) {
+        usize ta, tb;
+        if (j.plan->huge) {
+            if (j.inner != 1) DSC_LOG_FATAL("transforms of 2^%d points are supported along the last axis only", j.plan->cu.lg_n);
+            const usize es = j.plan->cu.dtype == DSC_CUDA_F32 ? sizeof(c32) : sizeof(c64);
+            ta = tb = (usize) j.plan->cu.n * es;
+        } else {
+            ta = (usize) j.inner * (usize) j.x_n * DSC_DTYPE_SIZE[j.x->dtype];
+            tb = (usize) j.inner * (usize) j.out_n * DSC_DTYPE_SIZE[j.out->dtype];
+        }
+        tmp_nodes[0] = ctx->dev_alloc.alloc(ta);
+        tmp_nodes[1] = ctx->dev_alloc.alloc(tb);
+        if (tmp_nodes[0] < 0 || tmp_nodes[1] < 0)
+            DSC_LOG_FATAL("device arena exhausted: this transform needs %.1fMB of temporaries", DSC_B_TO_MB(ta + tb));
+        jj.tmp_a = ctx->dev_base + ctx->dev_alloc.nodes[tmp_nodes[0]].off;
+        jj.tmp_b = ctx->dev_base + ctx->dev_alloc.nodes[tmp_nodes[1]].off;
+        // the sub-transforms are contiguous batches: size the work buffer for them
+        const dsc_cuda_plan *wp = j.plan->huge ? &j.sub1->cu : &j.plan->cu;
+        const i64 wl = j.plan->huge ? ((i64) 1 << j.plan->lg_h2) : j.inner;
+        usize need = dsc_cuda_work_bytes(wp, wl);
+        if (j.plan->huge) need = DSC_MAX(need, dsc_cuda_work_bytes(&j.sub2->cu, (i64) 1 << j.plan->lg_h1));
+        if (need > work_bytes) {
+            ctx->dev_scratch.reset();
+            work_bytes = DSC_MIN(need, ctx->dev_scratch.capacity) / DEV_GRANULE * DEV_GRANULE;
+            const usize off = ctx->dev_scratch.alloc(work_bytes, DEV_GRANULE);
+            DSC_ASSERT(off != (usize) -1);
+            work = ctx->dev_base + (ctx->dev_size - ctx->dev_scratch_size) + off;
+        }
+    }
+
     const bool tracing = dsc_trace_recording();
     for (i64 r0 = 0; r0 < j.outer; r0 += rows_per_chunk) {
         const i64 rows = DSC_MIN(rows_per_chunk, j.outer - r0);
@@ -528,7 +637,7 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
             }
         }
         dscdev::Event *k0 = tracing ? dscdev::event_record(0) : nullptr;
-        launch_chunk(ctx, j, dx, dout, r0, rows, work, work_bytes);
+        launch_chunk(ctx, jj, dx, dout, r0, rows, work, work_bytes);
         dscdev::Event *k1 = (tracing || download) ? dscdev::event_record(0) : nullptr;
         if (download) {
             dscdev::stream_wait(2, k1);
@@ -564,6 +673,11 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
     }
     bx->pad_ = bo->pad_ = 0;
     if (j.spectrum) j.spectrum->buffer->pad_ = 0;
+    if (tmp_nodes[0] >= 0) {
+        dscdev::stream_sync(0);
+        ctx->dev_alloc.release(tmp_nodes[0]);
+        ctx->dev_alloc.release(tmp_nodes[1]);
+    }
     if (ctx->residency == 0) {
         // strict mode: nothing stays behind on the device, every call starts from host memory
         dscdev::stream_sync(0);
@@ -625,6 +739,11 @@ dsc_tensor *dsc_internal_fft(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out,
     xform_job j{};
     j.kind = forward ? XF_FFT : XF_IFFT;
     j.plan = dsc_plan_fft(ctx, n, COMPLEX, out_dtype);
+    if (j.plan->huge) {
+        static_assert(DSC_MAX_FFT_PLANS >= 3, "a composed plan and its two sub-plans must fit the cache together");
+        j.sub1 = dsc_plan_fft(ctx, 1 << j.plan->lg_h1, COMPLEX, out_dtype);
+        j.sub2 = dsc_plan_fft(ctx, 1 << j.plan->lg_h2, COMPLEX, out_dtype);
+    }
     j.x = x; j.out = out;
     j.x_n = x_n; j.out_n = n;
     split_axis(x, axis_idx, &j.outer, &j.inner);

@@ -83,6 +83,12 @@ struct dsc_fft_plan {
     dsc_cuda_plan cu;               // n, type, dtype and the device tables
     int last_used;                  // ageing counter of the cache (dsc.cpp:199-213)
     int dev_node;
+    // Lengths beyond the kernels' four-step range (> 2^24 complex64 / 2^23 complex128 points) are
+    // composed on the host from two cached sub-plans n = h1 * h2, three transposes and this plan's own
+    // inter-pass twiddle tables (W_n^p split in two sqrt(n)-sized halves).
+    bool huge;
+    int lg_h1, lg_h2, h_shift;
+    void *h_lo, *h_hi;
 };
 
 struct dsc_ctx {

@@ -778,6 +778,59 @@ __global__ void transpose_twiddle(const cx<T> *__restrict__ in, cx<T> *__restric
     }
 }
 
+// Plain tiled transpose of rows x cols elements of any 4/8/16-byte type: out[c][r] = in[r][c].
+// (Transforms of more than one shared-memory pass along a NON-last axis are done as transpose,
+// last-axis transform, transpose.)
+template <typename U>
+__global__ void transpose_plain(const U *__restrict__ in, U *__restrict__ out, int rows, int cols) {
+    __shared__ U tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_c = (cols + 31) / 32;
+    const int c0 = (int)(blockIdx.x % tiles_c) * 32, r0 = (int)(blockIdx.x / tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int r = r0 + ty + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + i][tx] = in[(long long)r * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int c = c0 + ty + i, r = r0 + tx;
+        if (r < rows && c < cols) out[(long long)c * rows + r] = tile[tx][ty + i];
+    }
+}
+
+// First step of a transform too long for the four-step plan (> 2^24 points): the line, seen as
+// rows x cols, is transposed while being cast to complex and zero-padded past `limit` elements
+// (gather + cast + pad of /root/reference/dsc/src/dsc.cpp:1981-1994).
+template <typename T, bool IN_REAL>
+__global__ void transpose_cast_pad(const void *__restrict__ in, cx<T> *__restrict__ out, int rows, int cols, long long limit) {
+    using V = cx<T>;
+    __shared__ V tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_c = (cols + 31) / 32;
+    const int c0 = (int)(blockIdx.x % tiles_c) * 32, r0 = (int)(blockIdx.x / tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int r = r0 + ty + i, c = c0 + tx;
+        if (r < rows && c < cols) {
+            const long long idx = (long long)r * cols + c;
+            V v = mk<T>((T)0, (T)0);
+            if (idx < limit) {
+                if (IN_REAL) v.x = ((const T *)in)[idx];
+                else v = ((const V *)in)[idx];
+            }
+            tile[ty + i][tx] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int c = c0 + ty + i, r = r0 + tx;
+        if (r < rows && c < cols) out[(long long)c * rows + r] = tile[tx][ty + i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Frequency-domain pointwise product (mul_op, /root/reference/dsc/include/dsc_ops.h:68-78),
 // b broadcast over rows when b_rows == 0.

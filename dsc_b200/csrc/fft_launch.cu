@@ -637,4 +637,31 @@ int dsc_cuda_transpose_twiddle(const void *in, void *out, int64_t rows, int64_t 
     return check_launch("transpose_twiddle");
 }
 
+int dsc_cuda_transpose(const void *in, void *out, int64_t rows, int64_t cols, int elem_bytes, void *stream) {
+    if (!in || !out || rows <= 0 || cols <= 0 || rows > 0x7fffffff || cols > 0x7fffffff)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose: bad argument");
+    const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    if (tiles > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose: too many tiles");
+    if (elem_bytes == 4) { auto k = transpose_plain<float>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const float *)in, (float *)out, (int)rows, (int)cols); }
+    else if (elem_bytes == 8) { auto k = transpose_plain<float2>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const float2 *)in, (float2 *)out, (int)rows, (int)cols); }
+    else if (elem_bytes == 16) { auto k = transpose_plain<double2>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, (const double2 *)in, (double2 *)out, (int)rows, (int)cols); }
+    else return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose: element size %d", elem_bytes);
+    return check_launch("transpose_plain");
+}
+
+int dsc_cuda_transpose_cast(const void *in, int in_dtype, void *out, int64_t rows, int64_t cols, int64_t limit, void *stream) {
+    if (!in || !out || rows <= 0 || cols <= 0 || rows > 0x7fffffff || cols > 0x7fffffff)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_cast: bad argument");
+    const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    if (tiles > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_cast: too many tiles");
+    switch (in_dtype) {
+        case DSC_CUDA_F32: { auto k = transpose_cast_pad<float, true>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, in, (float2 *)out, (int)rows, (int)cols, (long long)limit); break; }
+        case DSC_CUDA_C32: { auto k = transpose_cast_pad<float, false>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, in, (float2 *)out, (int)rows, (int)cols, (long long)limit); break; }
+        case DSC_CUDA_F64: { auto k = transpose_cast_pad<double, true>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, in, (double2 *)out, (int)rows, (int)cols, (long long)limit); break; }
+        case DSC_CUDA_C64: { auto k = transpose_cast_pad<double, false>; DSC_LAUNCH(k, (unsigned)tiles, 256, 0, stream, in, (double2 *)out, (int)rows, (int)cols, (long long)limit); break; }
+        default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_cast: dtype %d", in_dtype);
+    }
+    return check_launch("transpose_cast_pad");
+}
+
 }  // extern "C"

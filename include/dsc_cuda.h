@@ -117,6 +117,13 @@ int dsc_cuda_transpose_twiddle(const void *in, void *out, int64_t rows, int64_t 
                                const void *tw_lo, const void *tw_hi, int shift, int forward,
                                int dtype, void *stream);
 
+/* out[c][r] = in[r][c] for rows x cols elements of elem_bytes in {4, 8, 16}. */
+int dsc_cuda_transpose(const void *in, void *out, int64_t rows, int64_t cols, int elem_bytes, void *stream);
+
+/* Transpose with cast to complex and zero padding: out[c][r] = (r*cols + c < limit) ? complex(in[r*cols + c]) : 0.
+ * in_dtype in {F32,F64,C32,C64}; out is complex of the same precision. */
+int dsc_cuda_transpose_cast(const void *in, int in_dtype, void *out, int64_t rows, int64_t cols, int64_t limit, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

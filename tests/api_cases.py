@@ -180,3 +180,28 @@ def check_traces(dsc):
     assert gpu and all(e["ph"] == "X" and e["dur"] >= 0 and e["args"]["n"] in (64, 32) for e in gpu)
     assert any(e["cat"] == "gpu;copy" for e in events)
     del y, r
+
+
+def check_composed_paths(dsc):
+    """Coverage beyond the kernels' direct range: (a) lengths of more than one shared-memory pass along a
+    NON-last axis (transpose, transform, transpose); (b) the host-composed plan used for lengths past the
+    four-step range, forced at a small size through the DSC_HUGE_LG testing knob."""
+    rng = np.random.default_rng(18)
+    x = randn(rng, (1 << 15, 3), "complex64")
+    got = dsc.fft(x, axis=0).numpy()
+    assert rel_l2(got, port.fft(x, axis=0)) < 1e-6
+    xr = randn(rng, (2, 1 << 16, 2), "float32")
+    X = dsc.rfft(xr, axis=1)
+    want = port.rfft(xr, -1, 1)
+    assert X.shape == want.shape and rel_l2(X.numpy(), want) < 1e-6
+    assert rel_l2(dsc.irfft(X, axis=1).numpy(), xr) < 1e-6
+    os.environ["DSC_HUGE_LG"] = "11"
+    try:
+        x = randn(rng, (2, 1 << 14), "complex64")
+        y = dsc.fft(x)
+        assert rel_l2(y.numpy(), port.fft(x)) < 1e-6
+        assert rel_l2(dsc.ifft(y).numpy(), x) < 1e-6
+        xs = randn(rng, (10000,), "float32")               # real input, zero-padded to 16384
+        assert rel_l2(dsc.fft(xs).numpy(), port.fft(xs)) < 1e-6
+    finally:
+        os.environ.pop("DSC_HUGE_LG", None)

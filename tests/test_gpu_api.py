@@ -23,7 +23,8 @@ def dsc():
 
 CASES = [api_cases.check_golden, api_cases.check_shapes_appendix_a, api_cases.check_out_param,
          api_cases.check_vs_oracle_sweep, api_cases.check_filter_pipeline, api_cases.check_plan_cache,
-         api_cases.check_memory_accounting, api_cases.check_residency_modes, api_cases.check_traces]
+         api_cases.check_memory_accounting, api_cases.check_residency_modes, api_cases.check_traces,
+         api_cases.check_composed_paths]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c.__name__ for c in CASES])
@@ -82,3 +83,20 @@ def test_config4_properties(dsc):
     unfused = dsc.irfft(dsc.rfft(s) * B).numpy()
     assert rel_l2(fused, unfused) < 1e-5
     assert rel_l2(fused[0], port.filter_fft(s[0], b, 1 << 20)) < 1e-5
+
+
+def test_huge_single_transform(dsc):
+    """2^25 complex64 points: past the four-step plan range, composed from 2^13 x 2^12 sub-plans.  The
+    oracle needs ~1 s for this size; sampled bins are also checked against a float64 DFT."""
+    rng = np.random.default_rng(25)
+    n = 1 << 25
+    x = randn(rng, (n,), "complex64")
+    y = dsc.fft(x).numpy()
+    want = port.fft(x)
+    assert rel_l2(y, want) < 1e-5
+    ks = [0, 1, 12345, n // 2, n - 1]
+    t = np.arange(n, dtype=np.float64)
+    for k in ks:
+        ref = np.sum(x.astype(np.complex128) * np.exp(-2j * np.pi * ((k * t) % n) / n))
+        assert abs(y[k] - ref) / abs(ref) < 1e-4
+    assert rel_l2(dsc.ifft(dsc.from_numpy(y)).numpy(), x) < 1e-5
