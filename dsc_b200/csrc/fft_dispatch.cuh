@@ -25,7 +25,12 @@ template <typename T> struct Tile;
 template <> struct Tile<float>  { static constexpr int LG_E = 4; static constexpr int MAX_LG = 14; static constexpr int COAL = 16; };
 template <> struct Tile<double> { static constexpr int LG_E = 3; static constexpr int MAX_LG = 13; static constexpr int COAL = 8; };
 
-template <typename T> constexpr int lg_e_for(int lg_n) { return lg_n < Tile<T>::LG_E ? lg_n : Tile<T>::LG_E; }
+// points per thread: radix-16 (float) / radix-8 (double) tiles; the longest float lines use radix-32 so
+// that three stages (two shared-memory exchanges) still cover them
+template <typename T> constexpr int lg_e_for(int lg_n) {
+    if (sizeof(T) == 4 && lg_n >= 13) return 5;
+    return lg_n < Tile<T>::LG_E ? lg_n : Tile<T>::LG_E;
+}
 
 constexpr int imin(int a, int b) { return a < b ? a : b; }
 constexpr int imax(int a, int b) { return a > b ? a : b; }
@@ -88,12 +93,13 @@ struct FusedEntry {
 
 // block size for a pair of pass lengths: both passes keep >= 64 contiguous bytes per access
 template <typename T> constexpr int fused_threads(int lg_n1, int lg_n2) {
+    if (sizeof(T) == 4 && lg_n1 >= 9 && lg_n2 >= 9) return 256;      // radix-32 tiles: 8+ lines of <= 32 threads
     return (lg_n1 > 8 || lg_n2 > 8) ? 512 : 256;
 }
 
 template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_threads<T>(LG_N1, LG_N2)>
 FusedEntry make_fused() {
-    constexpr int LG_E1 = lg_e_for<T>(LG_N1), LG_E2 = lg_e_for<T>(LG_N2);
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
     constexpr int SM_A = LPB_A * Sched<LG_N1, LG_E1>::line_stride(LPB_A, (int)sizeof(cx<T>));
     constexpr int SM_B = LPB_B * Sched<LG_N2, LG_E2>::line_stride(LPB_B, (int)sizeof(cx<T>));
@@ -124,10 +130,10 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
         for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
         return nullptr;                                                                    \
     }
-#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(), make_fused<float, true, A, B, 256>(),
-#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(), make_fused<float, false, A, B, 256>(),
-#define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B>(), make_fused<double, true, A, B, 256>(),
-#define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B>(), make_fused<double, false, A, B, 256>(),
+#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(),
+#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(),
+#define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B, 256>(),
+#define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B, 256>(),
 
 #define DSC_DEFINE_TABLE(T, FWD, MODE, SV)                                                        \
     template <> KernelEntry *get_table<T, FWD, MODE, SV>() {                                      \

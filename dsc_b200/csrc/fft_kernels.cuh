@@ -572,6 +572,16 @@ fft_lines(const FftArgs a) {
 // row is therefore consumed a few microseconds after it is produced and never leaves L2
 // (POL_L2 loads bypass the non-coherent L1; the payload itself streams with evict-first hints),
 // so HBM sees one read and one write per element although there are two passes.
+// points per thread of a four-step pass (must agree with lg_e_for in fft_dispatch.cuh for these lengths)
+template <typename T> __host__ __device__ constexpr int pass_lg_e(int lg_n, int lg_other) {
+    // float passes of 512 / 1024 points use radix-32 tiles when BOTH factors are that long: a line is then
+    // one warp (or half of one), its two stages exchange through shared memory under __syncwarp only, and
+    // there is one exchange instead of two (measured: 2^18-2^20 +5-10 %, 2^17 and below slower)
+    if (sizeof(T) == 4 && lg_n >= 9 && lg_other >= 9) return 5;
+    const int e = sizeof(T) == 4 ? 4 : 3;
+    return lg_n < e ? lg_n : e;
+}
+
 struct FourStepSync {
     unsigned *ticket;    // one counter
     unsigned *a_done;    // per row: first-pass blocks finished
@@ -592,8 +602,7 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
 template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
 __global__ void __launch_bounds__(THREADS)
 four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
-    constexpr int LG_E1 = LG_N1 < (sizeof(T) == 4 ? 4 : 3) ? LG_N1 : (sizeof(T) == 4 ? 4 : 3);
-    constexpr int LG_E2 = LG_N2 < (sizeof(T) == 4 ? 4 : 3) ? LG_N2 : (sizeof(T) == 4 ? 4 : 3);
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
     static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
     DSC_DYN_SMEM(smem_raw);

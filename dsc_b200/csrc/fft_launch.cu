@@ -47,9 +47,8 @@ struct SubSched {           // stage layout of one shared-memory pass of length 
     int ns[DSC_CUDA_MAX_STAGES], r[DSC_CUDA_MAX_STAGES];
 };
 
-SubSched sub_sched(int lg, int lg_e_max) {
+SubSched sub_sched(int lg, int lg_e) {
     SubSched s{};
-    const int lg_e = lg < lg_e_max ? lg : lg_e_max;
     s.stages = lg_e == 0 ? 1 : (lg + lg_e - 1) / lg_e;
     for (int i = 0; i < s.stages; ++i) {
         const int rem = lg - i * lg_e;
@@ -60,7 +59,7 @@ SubSched sub_sched(int lg, int lg_e_max) {
 }
 
 struct PlanLayout {
-    int lg_n, lg_n1, lg_n2, four_shift, real_shift;
+    int lg_n, lg_n1, lg_n2, four_shift, real_shift, lg_e1, lg_e2;
     size_t off_tw1[DSC_CUDA_MAX_STAGES], off_tw2[DSC_CUDA_MAX_STAGES];
     size_t off_lo, off_hi, off_real, off_real_lo, off_real_hi, total;
     bool ok;
@@ -76,12 +75,16 @@ template <typename T> PlanLayout plan_layout(int n, int fft_type) {
         L.lg_n1 = L.lg_n - L.lg_n2;
     }
     L.ok = L.lg_n1 <= Tile<T>::MAX_LG;
+    // tile size of the pass kernels: the fused launch (both factors <= 2^10) has its own choice
+    const bool fused = L.lg_n2 != 0 && L.lg_n1 <= 10 && L.lg_n2 <= 10;
+    L.lg_e1 = fused ? pass_lg_e<T>(L.lg_n1, L.lg_n2) : lg_e_for<T>(L.lg_n1);
+    L.lg_e2 = fused ? pass_lg_e<T>(L.lg_n2, L.lg_n1) : lg_e_for<T>(L.lg_n2);
     size_t off = 0;
     auto take = [&](size_t count) { const size_t o = off; off = align_up(off + count * es, 256); return o; };
-    const SubSched s1 = sub_sched(L.lg_n1, Tile<T>::LG_E);
+    const SubSched s1 = sub_sched(L.lg_n1, L.lg_e1);
     for (int s = 1; s < s1.stages; ++s) L.off_tw1[s] = take((size_t)(s1.r[s] - 1) * s1.ns[s]);
     if (L.lg_n2) {
-        const SubSched s2 = sub_sched(L.lg_n2, Tile<T>::LG_E);
+        const SubSched s2 = sub_sched(L.lg_n2, L.lg_e2);
         for (int s = 1; s < s2.stages; ++s) L.off_tw2[s] = take((size_t)(s2.r[s] - 1) * s2.ns[s]);
         L.four_shift = (L.lg_n + 1) / 2;
         L.off_lo = take((size_t)1 << L.four_shift);
@@ -113,13 +116,13 @@ int build_tables(dsc_cuda_plan *p, const PlanLayout &L, void *stream) {
         const int blocks = (int)((count + 255) / 256 < 1024 ? (count + 255) / 256 : 1024);
         DSC_LAUNCH(fill_power_twiddles<T>, blocks, 256, 0, stream, (V *)dst, count, mult, denom);
     };
-    const SubSched s1 = sub_sched(L.lg_n1, Tile<T>::LG_E);
+    const SubSched s1 = sub_sched(L.lg_n1, L.lg_e1);
     for (int s = 1; s < s1.stages; ++s) {
         p->tw1[s] = base + L.off_tw1[s];
         fill_stage(p->tw1[s], s1.ns[s], s1.r[s]);
     }
     if (L.lg_n2) {
-        const SubSched s2 = sub_sched(L.lg_n2, Tile<T>::LG_E);
+        const SubSched s2 = sub_sched(L.lg_n2, L.lg_e2);
         for (int s = 1; s < s2.stages; ++s) {
             p->tw2[s] = base + L.off_tw2[s];
             fill_stage(p->tw2[s], s2.ns[s], s2.r[s]);
@@ -275,6 +278,8 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         return check_launch("four_step_fused");
     }
 
+    if (fe != nullptr)
+        return fail(DSC_CUDA_ENOMEM, "work buffer too small for the fused four-step launch (n=%lld needs %zu bytes)", n, sync_bytes + row_bytes);
     // two launches per chunk of rows
     if (!work || work_bytes < row_bytes) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (n=%lld)", n);
     const long long chunk = (long long)(work_bytes / row_bytes);

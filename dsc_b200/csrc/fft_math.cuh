@@ -84,8 +84,8 @@ template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w16(cx<T> a) {
     constexpr T c1 = consts<T>::cos_pi_8, s1 = consts<T>::sin_pi_8;
     if (Q % 2 == 0) return mul_w8<FWD, (Q / 2) % 4, T>(Q >= 8 ? mk<T>(-a.x, -a.y) : a);
     // odd q: cos/sin of q*pi/8 from the pi/8 pair
-    constexpr T c = (Q == 1) ? c1 : (Q == 3) ? s1 : (Q == 5) ? -s1 : (Q == 7) ? -c1 : /*9*/ -c1;
-    constexpr T s = (Q == 1) ? s1 : (Q == 3) ? c1 : (Q == 5) ? c1 : (Q == 7) ? s1 : /*9*/ -s1;
+    constexpr T c = (Q == 1) ? c1 : (Q == 3) ? s1 : (Q == 5) ? -s1 : (Q == 7) ? -c1 : (Q == 9) ? -c1 : /*11*/ -s1;
+    constexpr T s = (Q == 1) ? s1 : (Q == 3) ? c1 : (Q == 5) ? c1 : (Q == 7) ? s1 : (Q == 9) ? -s1 : /*11*/ -c1;
     return FWD ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s)
                : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
 }
@@ -147,6 +147,61 @@ template <bool FWD, typename T> struct Dft<16, FWD, T> {
 #define DSC_SWAP(i, j) { const cx<T> s_ = v[i]; v[i] = v[j]; v[j] = s_; }
         DSC_SWAP(1, 4) DSC_SWAP(2, 8) DSC_SWAP(3, 12) DSC_SWAP(6, 9) DSC_SWAP(7, 13) DSC_SWAP(11, 14)
 #undef DSC_SWAP
+    }
+};
+
+// cos / sin of 2 pi q / 32 as compile-time constants (q in 0..31)
+template <typename T> struct w32 {
+    static constexpr double c_[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                     0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                                     0.19509032201612826785, 0.0};
+    static __host__ __device__ constexpr T cosq(int q) {
+        q &= 31;
+        if (q > 16) q = 32 - q;
+        return q <= 8 ? (T)c_[q] : (T)-c_[16 - q];
+    }
+    static __host__ __device__ constexpr T sinq(int q) {
+        q &= 31;
+        const bool neg = q > 16;
+        if (neg) q = 32 - q;
+        const T v = q <= 8 ? (T)c_[8 - q] : (T)c_[q - 8];
+        return neg ? -v : v;
+    }
+};
+
+// a * w32^q, w32 = e^{-+ 2 pi i / 32}
+template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w32(cx<T> a) {
+    if constexpr (Q % 2 == 0) return mul_w16<FWD, Q / 2, T>(a);
+    else {
+        constexpr T c = w32<T>::cosq(Q), s = w32<T>::sinq(Q);
+        return FWD ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s)
+                   : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
+    }
+}
+
+template <bool FWD, typename T> struct Dft<32, FWD, T> {
+    // m = 8a + b: eight DFT-4 over a, twiddle w32^{b p1}, four DFT-8 over b
+    static DSC_DEV void run(cx<T> (&v)[32]) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) bfly4<FWD>(v[b], v[b + 8], v[b + 16], v[b + 24]);
+        // v[b + 8 p1] = y_b[p1]
+#define DSC_TW(B, P) v[B + 8 * P] = mul_w32<FWD, B * P, T>(v[B + 8 * P]);
+        DSC_TW(1, 1) DSC_TW(2, 1) DSC_TW(3, 1) DSC_TW(4, 1) DSC_TW(5, 1) DSC_TW(6, 1) DSC_TW(7, 1)
+        DSC_TW(1, 2) DSC_TW(2, 2) DSC_TW(3, 2) DSC_TW(4, 2) DSC_TW(5, 2) DSC_TW(6, 2) DSC_TW(7, 2)
+        DSC_TW(1, 3) DSC_TW(2, 3) DSC_TW(3, 3) DSC_TW(4, 3) DSC_TW(5, 3) DSC_TW(6, 3) DSC_TW(7, 3)
+#undef DSC_TW
+        cx<T> out[32];
+#pragma unroll
+        for (int p1 = 0; p1 < 4; ++p1) {
+            cx<T> g[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) g[b] = v[8 * p1 + b];
+            Dft<8, FWD, T>::run(g);
+#pragma unroll
+            for (int p2 = 0; p2 < 8; ++p2) out[p1 + 4 * p2] = g[p2];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = out[i];
     }
 };
 
