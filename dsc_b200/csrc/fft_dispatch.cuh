@@ -130,8 +130,8 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
         for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
         return nullptr;                                                                    \
     }
-#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(),
-#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(),
+#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(), make_fused<float, true, A, B, 128>(),
+#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(), make_fused<float, false, A, B, 128>(),
 #define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B, 256>(),
 #define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B, 256>(),
 

@@ -245,7 +245,8 @@ template <int POL, typename V> DSC_DEV void st_pol(V *p, const V v) {
 // Body of one thread block: LPB lines starting at line `block * LPB`.
 // THREADS = LPB * TT.  Dynamic shared memory: LPB * Sched::LINE * sizeof(cx<T>).
 template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
-DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned char *smem_raw) {
+DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned char *smem_raw,
+                            const long long prefetch_block = -1) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
     constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, THREADS = LPB * TT;
@@ -342,6 +343,19 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
                 const T re = c * istep < tlim ? ld_pol<POL_IN>(src + c * istep) : (T)0;
                 const T im = c * istep + a.gi_pstride < tlim ? ld_pol<POL_IN>(src + c * istep + a.gi_pstride) : (T)0;
                 dst[Sc::pad_read(p0, pp0, c)] = mk<T>(re, im);
+            }
+        }
+        if (prefetch_block >= 0) {
+            // pull the tile that a block will need a few hundred tickets from now into L2, so that its demand
+            // loads hit L2 instead of waiting for HBM (DRAM bandwidth is not the limit of this pass, latency is)
+            const long long f0 = prefetch_block * LPB;
+            const long long fo = f0 >> a.inner_shift, fin0 = f0 & ((1LL << a.inner_shift) - 1);
+            const long long fbase = fo * a.gi.ostride + (fin0 + lt) * a.gi.lstride + (long long)p0 * a.gi.estride;
+            const size_t es = a.in_kind == IN_COMPLEX ? sizeof(V) : sizeof(T);
+            const char *fp = (const char *)a.x + (size_t)fbase * es;
+            if (lt == 0 || es * (size_t)a.gi.lstride * LPB > 128) {     // one prefetch per segment is enough
+#pragma unroll
+                for (int c = 0; c < E; ++c) dsc_prefetch_l2(fp + (size_t)(c * istep) * es);
             }
         }
         __syncthreads();
@@ -589,9 +603,25 @@ struct FourStepSync {
     int tiles_a, tiles_b;
     int ring;            // work rows (0 = one work row per top-level row, no reuse)
     int rows;
+    int prefetch;        // a first-pass block prefetches (to L2) the tile of the block this many tickets ahead
     int lag;             // ticket order: the B blocks of row r come after the A blocks of row r + lag, so
                          // that in steady state a B block finds its row already complete and never spins
 };
+
+// ticket -> (role, row, tile): A(0..lag-1), then groups { A(i + lag), B(i) }, then the last B rows
+DSC_DEV void decode_ticket(const FourStepSync &s, unsigned ticket, bool &role_a, unsigned &row, unsigned &r) {
+    const unsigned ta = (unsigned)s.tiles_a, tb = (unsigned)s.tiles_b, lag = (unsigned)s.lag;
+    if (ticket < lag * ta) { role_a = true; row = ticket / ta; r = ticket % ta; return; }
+    ticket -= lag * ta;
+    const unsigned full = (unsigned)s.rows - lag;
+    if (ticket < full * (ta + tb)) {
+        const unsigned i = ticket / (ta + tb), w = ticket % (ta + tb);
+        if (w < ta) { role_a = true; row = i + lag; r = w; } else { role_a = false; row = i; r = w - ta; }
+    } else {
+        ticket -= full * (ta + tb);
+        role_a = false; row = full + ticket / tb; r = ticket % tb;
+    }
+}
 
 DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
     const volatile unsigned *c = counter;
@@ -609,20 +639,17 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
     __shared__ unsigned ticket_s;
     if (threadIdx.x == 0) ticket_s = atomicAdd(s.ticket, 1u);
     __syncthreads();
-    // ticket -> (role, row, tile): A(0..lag-1), then groups { A(i + lag), B(i) }, then the last B rows
-    const unsigned ta = (unsigned)s.tiles_a, tb = (unsigned)s.tiles_b, lag = (unsigned)s.lag;
-    unsigned ticket = ticket_s, row, r;
+    unsigned row, r;
     bool role_a;
-    if (ticket < lag * ta) { role_a = true; row = ticket / ta; r = ticket % ta; }
-    else {
-        ticket -= lag * ta;
-        const unsigned full = (unsigned)s.rows - lag;
-        if (ticket < full * (ta + tb)) {
-            const unsigned i = ticket / (ta + tb), w = ticket % (ta + tb);
-            if (w < ta) { role_a = true; row = i + lag; r = w; } else { role_a = false; row = i; r = w - ta; }
-        } else {
-            ticket -= full * (ta + tb);
-            role_a = false; row = full + ticket / tb; r = ticket % tb;
+    decode_ticket(s, ticket_s, role_a, row, r);
+    // the first-pass block `prefetch` tickets ahead (if it is one): its tile goes to L2 now
+    long long pf_block = -1;
+    if (role_a && s.prefetch > 0) {
+        const unsigned long long tk = (unsigned long long)ticket_s + (unsigned)s.prefetch;
+        if (tk < (unsigned long long)s.rows * (unsigned)(s.tiles_a + s.tiles_b)) {
+            unsigned prow, pr; bool pa;
+            decode_ticket(s, (unsigned)tk, pa, prow, pr);
+            if (pa) pf_block = (long long)prow * s.tiles_a + pr;
         }
     }
     if (role_a) {
@@ -630,7 +657,7 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
             if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
             __syncthreads();
         }
-        fft_lines_body<T, LG_N1, LG_E1, LPB_A, FWD, MODE_PASS_A>(a, (long long)row * s.tiles_a + r, smem_raw);
+        fft_lines_body<T, LG_N1, LG_E1, LPB_A, FWD, MODE_PASS_A>(a, (long long)row * s.tiles_a + r, smem_raw, pf_block);
         __syncthreads();
         if (threadIdx.x == 0) { __threadfence(); atomicAdd(s.a_done + row, 1u); }
     } else {

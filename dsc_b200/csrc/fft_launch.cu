@@ -255,6 +255,10 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
             if (ring > 0 && lag > ring / 2) lag = ring / 2;
             if (lag > rows) lag = rows;
             s.lag = (int)lag;
+            // L2 prefetch of the first-pass tile `prefetch` tickets ahead: measured no gain on B200 (the pass is
+            // not waiting on DRAM latency), so it is off unless the knob asks for it
+            const char *pf = getenv("DSC_FUSED_PREFETCH");
+            s.prefetch = pf ? atoi(pf) : 0;
         }
         V *mid = (V *)((char *)work + sync_bytes);
         a.out = mid; a.lines = rows * n2; a.ring_out = ring; a.inner_shift = p->lg_n2;
@@ -273,6 +277,10 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
         if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
 #endif
+        if (const char *only = getenv("DSC_FUSED_ONLY")) {      // profiling knob: run one pass alone (results are garbage)
+            if (only[0] == 'A') s.tiles_b = 0;
+            if (only[0] == 'B') s.tiles_a = 0;
+        }
         const unsigned blocks = (unsigned)(rows * (s.tiles_a + s.tiles_b));
         DSC_LAUNCH(fe->fn, blocks, fe->threads, fe->smem, stream, a, b, s);
         return check_launch("four_step_fused");

@@ -28,6 +28,12 @@ __device__ __forceinline__ void dsc_named_barrier(int id, int count) {
 }
 #endif
 
+#if defined(DSC_EMUL)
+#define dsc_prefetch_l2(p) ((void)(p))
+#else
+__device__ __forceinline__ void dsc_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // dynamic shared memory of the running block
 #if defined(DSC_EMUL)
 #define DSC_DYN_SMEM(name) unsigned char *name = dsc_emul::tls.smem
