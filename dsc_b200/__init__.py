@@ -100,15 +100,6 @@ def _load():
     return L
 
 
-def _use_library(path: str) -> None:
-    """Tests only: drop the current context and bind another build of the same C ABI
-    (tests/emul/libdsc_emul.so runs the kernels on pthreads where there is no GPU)."""
-    global _lib, LIBDSC
-    shutdown()
-    _lib = None
-    LIBDSC = path
-
-
 def init(mem_size: int, scratch_size: int) -> None:
     """dsc.init(mem_size, scratch_size): two host arenas plus ONE device arena, made once."""
     global _ctx

@@ -8,6 +8,7 @@ import subprocess
 import pytest
 
 from tests import api_cases
+from tests.util import use_library
 
 EMUL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
 EMUL_SO = os.path.join(EMUL_DIR, "libdsc_emul.so")
@@ -17,7 +18,7 @@ EMUL_SO = os.path.join(EMUL_DIR, "libdsc_emul.so")
 def dsc():
     subprocess.run(["make", "-s", "-j8", "-C", EMUL_DIR], check=True)
     import dsc_b200
-    dsc_b200._use_library(EMUL_SO)
+    use_library(dsc_b200, EMUL_SO)
     os.environ["DSC_CHUNK_BYTES"] = str(1 << 16)       # force the multi-chunk transfer pipeline
     dsc_b200.init(1 << 28, 1 << 26)
     yield dsc_b200

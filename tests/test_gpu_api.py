@@ -6,6 +6,7 @@ import pytest
 
 from oracle import port
 from tests import api_cases
+from tests.util import use_library
 from tests.util import randn, rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -15,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def dsc():
     import dsc_b200
     from dsc_b200 import cuda_api
-    dsc_b200._use_library(cuda_api.LIBDSC)
+    use_library(dsc_b200, cuda_api.LIBDSC)
     dsc_b200.init(6 << 30, 1 << 30)
     yield dsc_b200
     dsc_b200.shutdown()

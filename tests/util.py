@@ -33,3 +33,11 @@ def load_golden():
     for i, m in enumerate(meta):
         arrs = {k: z[f"{k}{i}"] for k in ("x", "b", "y") if f"{k}{i}" in z.files}
         yield i, m, arrs
+
+
+def use_library(dsc, path):
+    """Point the dsc_b200 binding at another build of the same C ABI (tests only: the pthread-emulated
+    build where there is no GPU, the product build on the B200).  Drops the current context first."""
+    dsc.shutdown()
+    dsc._lib = None
+    dsc.LIBDSC = path
