@@ -29,6 +29,7 @@ template <> struct Tile<double> { static constexpr int LG_E = 3; static constexp
 // that three stages (two shared-memory exchanges) still cover them
 template <typename T> constexpr int lg_e_for(int lg_n) {
     if (sizeof(T) == 4 && lg_n >= 13) return 5;
+    if (sizeof(T) == 8 && lg_n >= 12) return 4;
     return lg_n < Tile<T>::LG_E ? lg_n : Tile<T>::LG_E;
 }
 
