@@ -219,7 +219,7 @@ void *dsc_dev_ptr(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
             dscdev::sync_all();
             for (dsc_tensor_buffer *b = ctx->dev_list; b != nullptr;) {
                 dsc_tensor_buffer *next = b->dev_next;
-                if (b->pad_ == 0) dsc_dev_drop(ctx, b);     // pad_ != 0 marks operands of the running op
+                if (b->busy == 0) dsc_dev_drop(ctx, b);     // pad_ != 0 marks operands of the running op
                 b = next;
             }
             node = ctx->dev_alloc.alloc(buf->nbytes);
@@ -279,7 +279,7 @@ DSC_MALLOC dsc_tensor *dsc_new_tensor(dsc_ctx *ctx, const int n_dim, const int *
         buffer->refs = 0;
         buffer->flags = ctx->use_scratch ? DSC_BUF_SCRATCH : 0;
         buffer->dev_node = -1;
-        buffer->pad_ = 0;
+        buffer->busy = 0;
         buffer->nbytes = nbytes;
         buffer->dev_prev = buffer->dev_next = nullptr;
     }
@@ -549,8 +549,8 @@ void upload_if_needed(dsc_ctx *ctx, const dsc_tensor *t) noexcept {
 void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
     dsc_tensor_buffer *bx = j.x->buffer, *bo = j.out->buffer;
     DSC_ASSERT(bx != bo);
-    bx->pad_ = bo->pad_ = 1;                                   // operands of the running op: not evictable
-    if (j.spectrum) j.spectrum->buffer->pad_ = 1;
+    bx->busy = bo->busy = 1;                                   // operands of the running op: not evictable
+    if (j.spectrum) j.spectrum->buffer->busy = 1;
 
     const bool x_on_device = ctx->residency >= 1 && bx->dev_node >= 0 && (bx->flags & DSC_BUF_DEV_VALID);
     const byte *dx = (const byte *) dsc_dev_ptr(ctx, bx);
@@ -671,8 +671,8 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
         bx->flags |= DSC_BUF_DEV_VALID;
         bo->flags |= DSC_BUF_DEV_VALID;
     }
-    bx->pad_ = bo->pad_ = 0;
-    if (j.spectrum) j.spectrum->buffer->pad_ = 0;
+    bx->busy = bo->busy = 0;
+    if (j.spectrum) j.spectrum->buffer->busy = 0;
     if (tmp_nodes[0] >= 0) {
         dscdev::stream_sync(0);
         ctx->dev_alloc.release(tmp_nodes[0]);

@@ -74,7 +74,7 @@ struct dsc_tensor_buffer {
     int refs;
     int flags;
     int dev_node;                   // block in the device arena, -1 = no mirror
-    int pad_;
+    int busy;                       // operand of the running op: its mirror must not be evicted
     usize nbytes;                   // payload bytes
     dsc_tensor_buffer *dev_prev, *dev_next;   // list of buffers that own a device mirror
 };
