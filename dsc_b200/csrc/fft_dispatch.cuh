@@ -56,7 +56,7 @@ KernelEntry make_entry() {
     e.fn = fft_lines<T, LG_N, LG_E, LPB, FWD, MODE>;
     e.lpb = LPB;
     e.threads = LPB * Sc::TT;
-    e.smem = LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>)) * (int)sizeof(cx<T>);
+    e.smem = LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>), MODE == MODE_FAST ? Sc::TT : 0) * (int)sizeof(cx<T>);
     e.configured = false;
     return e;
 }

@@ -91,9 +91,11 @@ template <int LG_N, int LG_E> struct Sched {
     // the next lanes are the next position: the line stride must map (line, position) pairs of one phase
     // (16 lanes of 8-byte elements, 8 lanes of 16-byte elements) onto distinct banks, i.e. be congruent
     // to phase/LPB modulo the phase.
-    static __host__ __device__ constexpr int line_stride(int lpb, int elem_bytes) {
+    // contiguous_tt > 0: the mapping is known to be "TT consecutive positions, then the next line" (MODE_FAST),
+    // and for short lines (TT < phase) a bank phase spans phase/TT lines: the stride must then be congruent to TT.
+    static __host__ __device__ constexpr int line_stride(int lpb, int elem_bytes, int contiguous_tt = 0) {
         const int phase = 128 / elem_bytes;
-        const int want = lpb >= phase ? 1 : phase / lpb;
+        const int want = (contiguous_tt > 0 && contiguous_tt < phase) ? contiguous_tt : lpb >= phase ? 1 : phase / lpb;
         const int base = N + (N >> LG_E);
         return base + ((want - base % phase) % phase + phase) % phase;
     }
@@ -261,7 +263,7 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     const int tid = threadIdx.x;
     int l, t;
     if (!TILED && a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
-    constexpr int LINE = Sc::line_stride(LPB, (int)sizeof(V));
+    constexpr int LINE = Sc::line_stride(LPB, (int)sizeof(V), MODE == MODE_FAST ? TT : 0);
     V *sm = sm_all + l * LINE;
     // A line's exchanges need: a warp barrier when the line lives inside one warp; its own hardware
     // barrier when it is a whole number of warps and the block has few enough lines (lines then
@@ -311,13 +313,25 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     // ---------------------------------------------------------------- load
     if constexpr (MODE == MODE_FAST) {
         // every line of the block exists and is dense: a.x / a.out are (lines, N) row-major
-        const V *__restrict__ xp = (const V *)a.x + line * N + t;
+        if constexpr (TT >= 4) {
+            const V *__restrict__ xp = (const V *)a.x + line * N + t;
 #pragma unroll
-        for (int c = 0; c < E; ++c) {
-            // with fewer than 32 threads per line a warp's accesses are only coalesced ACROSS the c loop:
-            // let L1 merge them; full warps per line stream past L1
-            if constexpr (TT >= 32) v[c] = ld_stream(xp + c * TT);
-            else v[c] = __ldcs(xp + c * TT);
+            for (int c = 0; c < E; ++c) {
+                // with fewer than 32 threads per line a warp's accesses are only coalesced ACROSS the c loop:
+                // let L1 merge them; full warps per line stream past L1
+                if constexpr (TT >= 32) v[c] = ld_stream(xp + c * TT);
+                else v[c] = __ldcs(xp + c * TT);
+            }
+        } else {
+            // short lines (a thread owns most of a line): the block's LPB lines are one contiguous run of
+            // LPB*N elements -- copy it coalesced into shared memory, then every thread picks up its points
+            const V *__restrict__ xb = (const V *)a.x + block * (long long)(LPB * N);
+            for (int e = tid; e < LPB * N; e += THREADS) sm_all[(e / N) * LINE + Sc::pad(e % N)] = __ldcs(xb + e);
+            __syncthreads();
+            const int pt = Sc::pad(t);
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
+            __syncthreads();
         }
     } else if constexpr (MODE == MODE_PASS_A) {
         // strided source tile -> shared memory (adjacent lanes = adjacent lines = contiguous bytes)
@@ -486,9 +500,19 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
 
     // ---------------------------------------------------------------- store
     if constexpr (MODE == MODE_FAST) {
-        V *__restrict__ op = (V *)a.out + line * N + t;
+        if constexpr (TT >= 4) {
+            V *__restrict__ op = (V *)a.out + line * N + t;
 #pragma unroll
-        for (int c = 0; c < E; ++c) st_stream(op + c * TT, v[c]);
+            for (int c = 0; c < E; ++c) st_stream(op + c * TT, v[c]);
+        } else {
+            __syncthreads();
+            const int pt = Sc::pad(t);
+#pragma unroll
+            for (int c = 0; c < E; ++c) sm[Sc::pad_read(t, pt, c)] = v[c];
+            __syncthreads();
+            V *__restrict__ ob = (V *)a.out + block * (long long)(LPB * N);
+            for (int e = tid; e < LPB * N; e += THREADS) st_stream(ob + e, sm_all[(e / N) * LINE + Sc::pad(e % N)]);
+        }
     } else if constexpr (TILED) {
         if (MODE == MODE_PASS_A && a.four_shift) {
             // times W_M^(q k1), q = this line's column n2, k1 = t + c*TT:  W^(q t) * W^(q TT c).
