@@ -449,6 +449,10 @@ dsc_tensor *binary(dsc_ctx *ctx, const char *name, dsc_tensor *xa, dsc_tensor *x
         DSC_ASSERT(memcmp(out->shape, shape, sizeof(shape)) == 0);
     }
 
+    if constexpr (std::is_same_v<Op, op_mul>) {
+        if (dsc_try_device_cmul(ctx, xa, xb, out)) return out;      // device-resident spectra stay on the device
+    }
+
     // operands are promoted through the scratch arena so nothing needs freeing afterwards
     dsc_ctx_push(ctx);
     const dsc_tensor *a = dsc_cast(ctx, xa, dtype);

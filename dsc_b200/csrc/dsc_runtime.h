@@ -123,6 +123,10 @@ void dsc_dev_drop(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept;               
 void dsc_host_written(dsc_tensor_buffer *buf) noexcept;                            // host op wrote the payload
 void dsc_host_needed(dsc_ctx *ctx, const dsc_tensor *x) noexcept;                  // host op is about to read the payload
 
+// Complex product on the device when an operand already lives there (residency >= 1): same shape or xb a
+// row broadcast over xa.  Returns false when the host loop should run instead.
+bool dsc_try_device_cmul(dsc_ctx *ctx, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept;
+
 // ---- tracer (dsc_trace.cpp) ---------------------------------------------------------------------
 void dsc_trace_init(u64 max_traces) noexcept;
 void dsc_trace_shutdown() noexcept;

@@ -148,6 +148,14 @@ def check_residency_modes(dsc):
             prod = y * y                      # host op on a device-resident tensor syncs it first
             assert rel_l2(prod.numpy(), port.fft(x) ** 2) < 1e-5
             del y, z, prod
+            # the README's three-call filter with the spectra staying on the device (row-broadcast product)
+            sig = randn(rng, (5, 1000), "float32")
+            taps = randn(rng, (37,), "float32")
+            S, B = dsc.rfft(sig, n=2048), dsc.rfft(taps, n=2048)
+            yf = dsc.irfft(S * B)
+            for r in range(5):
+                assert rel_l2(yf.numpy()[r], port.filter_fft(sig[r], taps, 2048)) < 1e-5
+            del S, B, yf
     finally:
         dsc.set_residency(0)
 
