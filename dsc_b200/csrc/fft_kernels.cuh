@@ -654,7 +654,7 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
 }
 
 template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1))
 four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
     constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
