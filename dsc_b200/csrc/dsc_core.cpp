@@ -285,6 +285,21 @@ bool dsc_try_device_cmul(dsc_ctx *ctx, const dsc_tensor *xa, const dsc_tensor *x
     return true;
 }
 
+bool dsc_try_device_crop(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, const int start, const int count) noexcept {
+    dsc_tensor_buffer *b = x->buffer;
+    if (!ctx->has_device || !(b->flags & DSC_BUF_HOST_STALE) || b->dev_node < 0) return false;
+    const usize es = DSC_DTYPE_SIZE[x->dtype];
+    const usize cols = (usize) x->shape[DSC_MAX_DIMS - 1];
+    const usize rows = cols > 0 ? (usize) x->ne / cols : 0;
+    if (rows == 0 || count <= 0) return false;
+    const byte *src = ctx->dev_base + ctx->dev_alloc.nodes[b->dev_node].off + (usize) start * es;
+    dscdev::stream_sync(0);                                   // the producer kernel must have finished
+    dscdev::copy_d2h_2d(out->data, (usize) count * es, src, cols * es, (usize) count * es, rows, 2);
+    dscdev::stream_sync(2);
+    dsc_host_written(out->buffer);
+    return true;
+}
+
 void dsc_cuda_set_residency(dsc_ctx *ctx, const int mode) noexcept {
     DSC_ASSERT(mode >= 0 && mode <= 2);
     if (mode < ctx->residency) {

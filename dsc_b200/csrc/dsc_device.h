@@ -31,6 +31,9 @@ void sync_all();
 
 void copy_h2d(void *dst_dev, const void *src_host, size_t bytes, int which_stream);
 void copy_d2h(void *dst_host, const void *src_dev, size_t bytes, int which_stream);
+// rows x width_bytes sub-matrix (pitches in bytes), device -> host
+void copy_d2h_2d(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch,
+                 size_t width_bytes, size_t rows, int which_stream);
 
 // Cross-stream ordering and timing.
 Event *event_record(int which_stream);          // from a small recycled pool

@@ -87,6 +87,11 @@ void copy_d2h(void *dst, const void *src, size_t bytes, int which) {
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_streams[which]));
 }
 
+void copy_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, int which) {
+    ensure_streams();
+    CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, g_streams[which]));
+}
+
 Event *event_record(int which) {
     ensure_streams();
     Event *e;

@@ -348,7 +348,6 @@ dsc_tensor *dsc_tensor_get_slice(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x,
     DSC_ASSERT((unsigned) slices <= (unsigned) DSC_MAX_DIMS);
     if (slices > x->n_dim) DSC_LOG_FATAL("too many slices");
     dsc_span span("dsc_tensor_get_slice", "slice;get", nullptr);
-    dsc_host_needed(ctx, x);
 
     dsc_slice raw[DSC_MAX_DIMS] = {};
     std::va_list args;
@@ -363,6 +362,15 @@ dsc_tensor *dsc_tensor_get_slice(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x,
         if (!sp[i].collapse) out_shape[out_ndim++] = sp[i].count;
     if (out_ndim == 0) { out_shape[0] = 1; out_ndim = 1; }
     dsc_tensor *out = dsc_new_tensor(ctx, out_ndim, out_shape, x->dtype);
+    // contiguous crop of the last axis with every other axis whole: if the data only lives on the device,
+    // download just the kept columns instead of the whole tensor
+    bool last_axis_crop = !sp[x->n_dim - 1].collapse && sp[x->n_dim - 1].step == 1;
+    for (int i = 0; i < x->n_dim - 1; ++i)
+        last_axis_crop = last_axis_crop && !sp[i].collapse && sp[i].start == 0 && sp[i].step == 1 &&
+                         sp[i].count == x->shape[dsc_tensor_dim(x, i)];
+    if (last_axis_crop && dsc_try_device_crop(ctx, x, out, sp[x->n_dim - 1].start, sp[x->n_dim - 1].count)) return out;
+
+    dsc_host_needed(ctx, x);
     const usize es = DSC_DTYPE_SIZE[x->dtype];
     for_each_selected(x, sp, [&](const int i, const int off) {
         memcpy((byte *) out->data + (usize) i * es, (const byte *) x->data + (usize) off * es, es);

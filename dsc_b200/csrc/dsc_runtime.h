@@ -127,6 +127,11 @@ void dsc_host_needed(dsc_ctx *ctx, const dsc_tensor *x) noexcept;               
 // row broadcast over xa.  Returns false when the host loop should run instead.
 bool dsc_try_device_cmul(dsc_ctx *ctx, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept;
 
+// Crop along the last axis of a tensor whose current contents live only on the device (residency 2): download
+// just the kept columns [start, start + count) of every row into `out` (the README's y[:output_length] after
+// irfft, README.md:133).  Returns false when the generic host path should run.
+bool dsc_try_device_crop(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, int start, int count) noexcept;
+
 // ---- tracer (dsc_trace.cpp) ---------------------------------------------------------------------
 void dsc_trace_init(u64 max_traces) noexcept;
 void dsc_trace_shutdown() noexcept;

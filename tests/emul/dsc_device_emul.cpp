@@ -30,6 +30,9 @@ void stream_sync(int) {}
 void sync_all() {}
 void copy_h2d(void *d, const void *s, size_t n, int) { memcpy(d, s, n); }
 void copy_d2h(void *d, const void *s, size_t n, int) { memcpy(d, s, n); }
+void copy_d2h_2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t rows, int) {
+    for (size_t r = 0; r < rows; ++r) memcpy((char *)d + r * dp, (const char *)s + r * sp, w);
+}
 Event *event_record(int) { return new Event{now_ms()}; }
 void stream_wait(int, Event *) {}
 float event_ms(Event *a, Event *b) { return (float)(b->t - a->t); }
