@@ -125,14 +125,11 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
 #define DSC_DEFINE_FUSED(T, FWD)                                                           \
     template <> FusedEntry *fused_entry<T, FWD>(int lg_n1, int lg_n2) {                    \
         static FusedEntry table[] = {DSC_FUSED_PAIRS(DSC_FUSED_MAKE_##FWD##_##T)};         \
-        const char *pref = getenv("DSC_FUSED_THREADS");   /* tuning knob: 256 | 512 */         \
-        const int want = pref ? atoi(pref) : 0;                                            \
-        for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2 && (!want || e.threads == want)) return &e; \
         for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
         return nullptr;                                                                    \
     }
-#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(), make_fused<float, true, A, B, 128>(),
-#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(), make_fused<float, false, A, B, 128>(),
+#define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(),
+#define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(),
 #define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B, 256>(),
 #define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B, 256>(),
 

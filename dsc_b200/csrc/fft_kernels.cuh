@@ -653,8 +653,15 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
     __threadfence();
 }
 
+// resident blocks per SM the register allocation must allow: radix-32 tiles (64 payload registers) fit two
+// 256-thread blocks; radix-16 / radix-8 tiles stay at <= 64 registers (four 256-thread or two 512-thread blocks)
+template <typename T> __host__ __device__ constexpr int fused_min_blocks(int lg_n1, int lg_n2, int threads) {
+    const bool wide = pass_lg_e<T>(lg_n1, lg_n2) == 5 || pass_lg_e<T>(lg_n2, lg_n1) == 5;
+    return wide ? (threads <= 256 ? 2 : 1) : (2048 / threads > 4 ? 4 : 1024 / threads);
+}
+
 template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(THREADS, fused_min_blocks<T>(LG_N1, LG_N2, THREADS))
 four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
     constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);

@@ -277,10 +277,6 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
         if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
 #endif
-        if (const char *only = getenv("DSC_FUSED_ONLY")) {      // profiling knob: run one pass alone (results are garbage)
-            if (only[0] == 'A') s.tiles_b = 0;
-            if (only[0] == 'B') s.tiles_a = 0;
-        }
         const unsigned blocks = (unsigned)(rows * (s.tiles_a + s.tiles_b));
         DSC_LAUNCH(fe->fn, blocks, fe->threads, fe->smem, stream, a, b, s);
         return check_launch("four_step_fused");
