@@ -89,13 +89,14 @@ DSC_DECLARE_TABLE(double, true, MODE_FAST, false) DSC_DECLARE_TABLE(double, fals
 struct FusedEntry {
     void (*fn)(const FftArgs, const FftArgs, const FourStepSync);
     int lg_n1, lg_n2, threads, lpb_a, lpb_b, smem;
+    int grid;            // persistent launch: resident blocks on the whole device (set when first configured)
     bool configured;
 };
 
-// block size for a pair of pass lengths: both passes keep >= 64 contiguous bytes per access
+// block size of the fused launch: 64 payload registers per thread, two blocks per SM
 template <typename T> constexpr int fused_threads(int lg_n1, int lg_n2) {
-    if (sizeof(T) == 4 && lg_n1 >= 9 && lg_n2 >= 9) return 256;      // radix-32 tiles: 8+ lines of <= 32 threads
-    return (lg_n1 > 8 || lg_n2 > 8) ? 512 : 256;
+    (void)lg_n1; (void)lg_n2;
+    return 256;
 }
 
 template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_threads<T>(LG_N1, LG_N2)>
@@ -108,6 +109,7 @@ FusedEntry make_fused() {
     e.fn = four_step_fused<T, LG_N1, LG_N2, THREADS, FWD>;
     e.lg_n1 = LG_N1; e.lg_n2 = LG_N2; e.threads = THREADS; e.lpb_a = LPB_A; e.lpb_b = LPB_B;
     e.smem = ((SM_A + LPB_A * (1 << LG_E1)) > SM_B ? (SM_A + LPB_A * (1 << LG_E1)) : SM_B) * (int)sizeof(cx<T>);   // + W^(q TT c) tables
+    e.grid = 0;
     e.configured = false;
     return e;
 }
@@ -130,8 +132,8 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
     }
 #define DSC_FUSED_MAKE_true_float(A, B) make_fused<float, true, A, B>(),
 #define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(),
-#define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B, 256>(),
-#define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B, 256>(),
+#define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B>(),
+#define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B>(),
 
 #define DSC_DEFINE_TABLE(T, FWD, MODE, SV)                                                        \
     template <> KernelEntry *get_table<T, FWD, MODE, SV>() {                                      \

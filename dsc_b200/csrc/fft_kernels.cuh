@@ -131,6 +131,13 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
     static constexpr bool LAST = (S == Sc::STAGES - 1);
 
     static DSC_DEV void run(V (&v)[E], V *sm, const int t, const FftArgs &a, const LineSync &ls) {
+        run(v, sm, t, sm, t, a, ls);
+    }
+    // (sm_r, t_r): the line buffer and position this thread continues with AFTER this stage's exchange.  The
+    // exchange is a free permutation point: a thread may come back as a different (line, position) of the
+    // block -- the four-step second pass reads contiguous rows one line per warp and writes with adjacent
+    // lanes on adjacent lines.  Needs a block-wide barrier when the two differ.
+    static DSC_DEV void run(V (&v)[E], V *sm, const int t, V *sm_r, const int t_r, const FftArgs &a, const LineSync &ls) {
         const V *__restrict__ tw = (const V *)a.tw[S];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -162,11 +169,11 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
         }
         if constexpr (!LAST) {
             line_sync(ls);
-            const int pt = Sc::pad(t);
+            const int pt = Sc::pad(t_r);
 #pragma unroll
-            for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
-            line_sync(ls);
-            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm, t, a, ls);
+            for (int c = 0; c < E; ++c) v[c] = sm_r[Sc::pad_read(t_r, pt, c)];
+            if constexpr (S + 1 < Sc::STAGES - 1) line_sync(ls);     // the next stage scatters into the same buffer
+            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm_r, t_r, sm_r, t_r, a, ls);
         }
     }
 };
@@ -598,6 +605,127 @@ fft_lines(const FftArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Register-direct tiles for the two passes of the four-step transform.
+//
+// Both passes are bound by the SM's load/store pipe (shared-memory wavefronts + L1 requests), not by HBM:
+// every trip of an element through shared memory costs as much pipe time as its trip to HBM.  So a tile here
+// touches shared memory ONLY for the exchanges between butterfly stages (one exchange for float lines up to
+// 1024 points: radix-32 x radix-32), and both global sides go straight between registers and memory:
+//
+//   first pass   L adjacent columns per block, thread = (line l = tid % L, position j = tid / L): a warp's
+//                load of element j + c*TT covers L*sizeof(V) contiguous bytes per position (64 B+), the same
+//                for its store of k1 = j + c*TT into the work row [k1][n2];
+//   second pass  reads its L contiguous work rows one line per (part of a) warp (lane = position), and at
+//                the first exchange the threads come back as (l = tid % L, j = tid / L), so the store of
+//                k2 = j + c*TT at k1 + n1*k2 again covers L adjacent k1 per position.
+//
+// The inter-pass twiddle W_n^(q k1), k1 = j + c*TT, is W^(q j) (one two-table lookup per thread) times
+// W^(q TT c), which depends on (line, c) only: L*E values per tile, built by the block into shared memory
+// once and read back as broadcasts.
+template <typename T, int LG_N, int LG_E, int L, bool FWD>
+DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, unsigned char *smem_raw) {
+    using Sc = Sched<LG_N, LG_E>;
+    using V = cx<T>;
+    constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
+    static_assert(Sc::STAGES >= 2, "the inter-pass table is published by the first exchange barrier");
+    constexpr int LINE = Sc::line_stride(L, (int)sizeof(V));
+    V *sm_all = (V *)smem_raw;
+    const int tid = threadIdx.x, l = tid % L, j = tid / L;
+    V *sm = sm_all + l * LINE;
+    V *tw_c = sm_all + L * LINE;                      // [c][l]
+    const LineSync ls{SYNC_BLOCK, 0, THREADS};
+
+    const long long line0 = tile * L;
+    const long long row = line0 >> a.inner_shift;
+    const unsigned q0 = (unsigned)(line0 & ((1LL << a.inner_shift) - 1)), q = q0 + (unsigned)l;
+    if (a.four_shift) {
+        for (int i = tid; i < L * E; i += THREADS) {
+            const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
+            tw_c[i] = four_step_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
+        }
+    }
+    const long long row_in = a.ring_in ? row % a.ring_in : row;
+    const long long row_out = a.ring_out ? row % a.ring_out : row;
+    const long long sbase = row_in * a.gi.ostride + (long long)q * a.gi.lstride + (long long)j * a.gi.estride;
+    const long long istep = (long long)TT * a.gi.estride;
+    const long long tlim = a.in_limit - (long long)q * a.gi.lstride - (long long)j * a.gi.estride;
+
+    V v[E];
+    if (a.in_kind == IN_COMPLEX) {
+        const V *__restrict__ src = (const V *)a.x + sbase;
+        if (a.no_limit) {
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = __ldcs(src + c * istep);
+        } else {
+            const V zero = mk<T>((T)0, (T)0);
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = c * istep < tlim ? __ldcs(src + c * istep) : zero;
+        }
+    } else if (a.in_kind == IN_REAL) {
+        const T *__restrict__ src = (const T *)a.x + sbase;
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = mk<T>(c * istep < tlim ? __ldcs(src + c * istep) : (T)0, (T)0);
+    } else {  // IN_PAIRS
+        const T *__restrict__ src = (const T *)a.x + sbase;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const T re = c * istep < tlim ? __ldcs(src + c * istep) : (T)0;
+            const T im = c * istep + a.gi_pstride < tlim ? __ldcs(src + c * istep + a.gi_pstride) : (T)0;
+            v[c] = mk<T>(re, im);
+        }
+    }
+
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, j, a, ls);
+
+    if (a.four_shift) {
+        const V w0 = four_step_twiddle<T>(a, q * (unsigned)j);
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], c == 0 ? w0 : cmul(w0, tw_c[c * L + l]));
+    }
+    V *__restrict__ op = (V *)a.out + row_out * a.go.ostride + (long long)q * a.go.lstride + (long long)j * a.go.estride;
+    const long long ostep = (long long)TT * a.go.estride;
+#pragma unroll
+    for (int c = 0; c < E; ++c) op[c * ostep] = v[c];          // stays in L2 for the second pass
+}
+
+template <typename T, int LG_N, int LG_E, int L, bool FWD>
+DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned char *smem_raw) {
+    using Sc = Sched<LG_N, LG_E>;
+    using V = cx<T>;
+    constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
+    static_assert(Sc::STAGES >= 2, "the threads change lines at the first exchange");
+    constexpr int LINE = Sc::line_stride(L, (int)sizeof(V));
+    V *sm_all = (V *)smem_raw;
+    const int tid = threadIdx.x;
+    const int l1 = tid / TT, j1 = tid % TT;           // while loading: one line per TT consecutive threads
+    const int l2 = tid % L, j2 = tid / L;             // after the first exchange: adjacent lanes, adjacent lines
+    const LineSync ls{SYNC_BLOCK, 0, THREADS};
+
+    const long long line0 = tile * L;
+    const long long row = line0 >> b.inner_shift;
+    const long long k0 = line0 & ((1LL << b.inner_shift) - 1);
+    const long long row_in = b.ring_in ? row % b.ring_in : row;
+    const long long row_out = b.ring_out ? row % b.ring_out : row;
+
+    V v[E];
+    const V *__restrict__ src = (const V *)b.x + row_in * b.gi.ostride + (k0 + l1) * b.gi.lstride + j1;
+#pragma unroll
+    for (int c = 0; c < E; ++c) v[c] = __ldcg(src + c * TT);      // written a moment ago by other SMs: L2 loads
+
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm_all + l1 * LINE, j1, sm_all + l2 * LINE, j2, b, ls);
+
+    if (b.do_scale) {
+        const T s = (T)b.scale;
+#pragma unroll
+        for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
+    }
+    V *__restrict__ op = (V *)b.out + row_out * b.go.ostride + (k0 + l2) * b.go.lstride + (long long)j2 * b.go.estride;
+    const long long ostep = (long long)TT * b.go.estride;
+#pragma unroll
+    for (int c = 0; c < E; ++c) __stcs(op + c * ostep, v[c]);
+}
+
+// ------------------------------------------------------------------------------------------
 // Four-step transform n = n1*n2 as ONE launch.
 //
 // Per top-level line ("row") there are TA first-pass blocks (length-n1 transforms over stride-n2
@@ -612,11 +740,10 @@ fft_lines(const FftArgs a) {
 // so HBM sees one read and one write per element although there are two passes.
 // points per thread of a four-step pass (must agree with lg_e_for in fft_dispatch.cuh for these lengths)
 template <typename T> __host__ __device__ constexpr int pass_lg_e(int lg_n, int lg_other) {
-    // float passes of 512 / 1024 points use radix-32 tiles when BOTH factors are that long: a line is then
-    // one warp (or half of one), its two stages exchange through shared memory under __syncwarp only, and
-    // there is one exchange instead of two (measured: 2^18-2^20 +5-10 %, 2^17 and below slower)
-    if (sizeof(T) == 4 && lg_n >= 9 && lg_other >= 9) return 5;
-    const int e = sizeof(T) == 4 ? 4 : 3;
+    // register-direct tiles: radix-32 (float) / radix-16 (double) register tiles, so that float lines of up to
+    // 1024 points need ONE shared-memory exchange
+    (void)lg_other;
+    const int e = sizeof(T) == 4 ? 5 : 4;
     return lg_n < e ? lg_n : e;
 }
 
@@ -653,50 +780,46 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
     __threadfence();
 }
 
-// resident blocks per SM the register allocation must allow: radix-32 tiles (64 payload registers) fit two
-// 256-thread blocks; radix-16 / radix-8 tiles stay at <= 64 registers (four 256-thread or two 512-thread blocks)
-template <typename T> __host__ __device__ constexpr int fused_min_blocks(int lg_n1, int lg_n2, int threads) {
-    const bool wide = pass_lg_e<T>(lg_n1, lg_n2) == 5 || pass_lg_e<T>(lg_n2, lg_n1) == 5;
-    return wide ? (threads <= 256 ? 2 : 1) : (2048 / threads > 4 ? 4 : 1024 / threads);
-}
-
+// Persistent blocks (the grid is what fits on the GPU at once): a block keeps taking tickets until none is
+// left, and asks for its NEXT ticket before it starts on the current tile, so the round trip of that atomic
+// -- like every other per-tile latency that is not payload -- overlaps the tile's own work.
 template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
-__global__ void __launch_bounds__(THREADS, fused_min_blocks<T>(LG_N1, LG_N2, THREADS))
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
     constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
     static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
     DSC_DYN_SMEM(smem_raw);
     __shared__ unsigned ticket_s;
+    const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
     if (threadIdx.x == 0) ticket_s = atomicAdd(s.ticket, 1u);
     __syncthreads();
-    unsigned row, r;
-    bool role_a;
-    decode_ticket(s, ticket_s, role_a, row, r);
-    // the first-pass block `prefetch` tickets ahead (if it is one): its tile goes to L2 now
-    long long pf_block = -1;
-    if (role_a && s.prefetch > 0) {
-        const unsigned long long tk = (unsigned long long)ticket_s + (unsigned)s.prefetch;
-        if (tk < (unsigned long long)s.rows * (unsigned)(s.tiles_a + s.tiles_b)) {
-            unsigned prow, pr; bool pa;
-            decode_ticket(s, (unsigned)tk, pa, prow, pr);
-            if (pa) pf_block = (long long)prow * s.tiles_a + pr;
-        }
-    }
-    if (role_a) {
-        if (s.ring && row >= (unsigned)s.ring) {
-            if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
+    unsigned ticket = ticket_s;
+    while (ticket < total) {
+        unsigned next = 0;
+        if (threadIdx.x == 0) next = atomicAdd(s.ticket, 1u);
+        unsigned row, r;
+        bool role_a;
+        decode_ticket(s, ticket, role_a, row, r);
+        if (role_a) {
+            if (s.ring && row >= (unsigned)s.ring) {
+                if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
+                __syncthreads();
+            }
+            pass_first_tile<T, LG_N1, LG_E1, LPB_A, FWD>(a, (long long)row * s.tiles_a + r, smem_raw);
+        } else {
+            if (threadIdx.x == 0) spin_until(s.a_done + row, (unsigned)s.tiles_a);
             __syncthreads();
+            pass_second_tile<T, LG_N2, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw);
         }
-        fft_lines_body<T, LG_N1, LG_E1, LPB_A, FWD, MODE_PASS_A>(a, (long long)row * s.tiles_a + r, smem_raw, pf_block);
+        __syncthreads();          // every store of the tile is issued; shared memory is free again
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd((role_a ? s.a_done : s.b_done) + row, 1u);
+            ticket_s = next;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); atomicAdd(s.a_done + row, 1u); }
-    } else {
-        if (threadIdx.x == 0) spin_until(s.a_done + row, (unsigned)s.tiles_a);
-        __syncthreads();
-        fft_lines_body<T, LG_N2, LG_E2, LPB_B, FWD, MODE_PASS_B>(b, (long long)row * s.tiles_b + r, smem_raw);
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); atomicAdd(s.b_done + row, 1u); }
+        ticket = ticket_s;
     }
 }
 

@@ -236,6 +236,24 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         const long long cap = (long long)(l2_budget / row_bytes) > 4 ? (long long)(l2_budget / row_bytes) : 4;
         if (ring > cap) ring = cap;
         if (ring >= rows) ring = 0;
+#if defined(DSC_EMUL)
+        fe->grid = 3;
+#else
+        if (!fe->configured) {
+            if (fe->smem > 48 * 1024) {
+                const cudaError_t err = cudaFuncSetAttribute((const void *)fe->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fe->smem);
+                if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
+            }
+            // persistent grid: every block that can be resident at once
+            int per_sm = 0, dev = 0, sms = 0;
+            cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fe->fn, fe->threads, fe->smem);
+            if (err == cudaSuccess) err = cudaGetDevice(&dev);
+            if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (err != cudaSuccess || per_sm < 1) return fail(DSC_CUDA_ELAUNCH, "occupancy query: %s", cudaGetErrorString(err));
+            fe->grid = per_sm * sms;
+            fe->configured = true;
+        }
+#endif
         FourStepSync s{};
         s.ticket = (unsigned *)work;
         s.a_done = s.ticket + 1;
@@ -247,7 +265,7 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         // lag (in rows) between a row's first and second pass in ticket order: about two grids' worth of
         // resident blocks, so second-pass blocks start on rows that are already complete; below the ring
         {
-            const long long resident = 148LL * (2048 / fe->threads);
+            const long long resident = fe->grid;
             long long lag = (2 * resident + s.tiles_a + s.tiles_b - 1) / (s.tiles_a + s.tiles_b);
             if (lag < 1) lag = 1;
             // ... and at most half the ring, so a first-pass block that reuses a work row finds the
@@ -267,17 +285,11 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
 #if defined(DSC_EMUL)
         memset(work, 0, sync_bytes);
 #else
-        if (!fe->configured) {
-            if (fe->smem > 48 * 1024) {
-                const cudaError_t err = cudaFuncSetAttribute((const void *)fe->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fe->smem);
-                if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
-            }
-            fe->configured = true;
-        }
         const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
         if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
 #endif
-        const unsigned blocks = (unsigned)(rows * (s.tiles_a + s.tiles_b));
+        const long long tiles = rows * (s.tiles_a + s.tiles_b);
+        const unsigned blocks = (unsigned)(tiles < fe->grid ? tiles : fe->grid);
         DSC_LAUNCH(fe->fn, blocks, fe->threads, fe->smem, stream, a, b, s);
         return check_launch("four_step_fused");
     }
