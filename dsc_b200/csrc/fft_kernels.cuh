@@ -622,8 +622,8 @@ fft_lines(const FftArgs a) {
 // The inter-pass twiddle W_n^(q k1), k1 = j + c*TT, is W^(q j) (one two-table lookup per thread) times
 // W^(q TT c), which depends on (line, c) only: L*E values per tile, built by the block into shared memory
 // once and read back as broadcasts.
-template <typename T, int LG_N, int LG_E, int L, bool FWD>
-DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, unsigned char *smem_raw) {
+template <typename T, int LG_N, int LG_E, int L, bool FWD, typename Hook>
+DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, unsigned char *smem_raw, Hook &&loads_in_flight) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
     constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
@@ -675,6 +675,7 @@ DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, unsigned ch
         }
     }
 
+    loads_in_flight();
     Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, j, a, ls);
 
     if (a.four_shift) {
@@ -688,8 +689,8 @@ DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, unsigned ch
     for (int c = 0; c < E; ++c) op[c * ostep] = v[c];          // stays in L2 for the second pass
 }
 
-template <typename T, int LG_N, int LG_E, int L, bool FWD>
-DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned char *smem_raw) {
+template <typename T, int LG_N, int LG_E, int L, bool FWD, typename Hook>
+DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned char *smem_raw, Hook &&loads_in_flight) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
     constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
@@ -712,6 +713,7 @@ DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned c
 #pragma unroll
     for (int c = 0; c < E; ++c) v[c] = __ldcg(src + c * TT);      // written a moment ago by other SMs: L2 loads
 
+    loads_in_flight();
     Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm_all + l1 * LINE, j1, sm_all + l2 * LINE, j2, b, ls);
 
     if (b.do_scale) {
@@ -781,8 +783,14 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
 }
 
 // Persistent blocks (the grid is what fits on the GPU at once): a block keeps taking tickets until none is
-// left, and asks for its NEXT ticket before it starts on the current tile, so the round trip of that atomic
-// -- like every other per-tile latency that is not payload -- overlaps the tile's own work.
+// left.  Everything per tile that is not payload is taken off the block's critical path by thread 0:
+//   * the NEXT ticket is requested before the current tile starts;
+//   * once the current tile's payload loads are in flight, the dependency flag of the next tile is read, so
+//     that (with the ticket lag it is almost always already satisfied) the next tile starts without a poll;
+//   * the release of the finished tile (fence + counter) happens AFTER the barrier that ends the tile, while
+//     the other warps are already loading the next one.
+// A flag observed satisfied is followed by a block barrier and then by L2 (.cg) loads of the dependent data,
+// which the producer made visible at L2 before it incremented the flag.
 template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS)
 four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
@@ -790,36 +798,48 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
     static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
     DSC_DYN_SMEM(smem_raw);
-    __shared__ unsigned ticket_s;
+    __shared__ unsigned next_ticket_s, next_ready_s;
     const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
-    if (threadIdx.x == 0) ticket_s = atomicAdd(s.ticket, 1u);
+    if (threadIdx.x == 0) { next_ticket_s = atomicAdd(s.ticket, 1u); next_ready_s = 0; }
     __syncthreads();
-    unsigned ticket = ticket_s;
-    while (ticket < total) {
-        unsigned next = 0;
+    while (true) {
+        const unsigned ticket = next_ticket_s, ready = next_ready_s;
+        if (ticket >= total) break;
+        unsigned next = 0, flag = 0, target = 0;
         if (threadIdx.x == 0) next = atomicAdd(s.ticket, 1u);
         unsigned row, r;
         bool role_a;
         decode_ticket(s, ticket, role_a, row, r);
-        if (role_a) {
-            if (s.ring && row >= (unsigned)s.ring) {
-                if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
+        if (!ready) {
+            if (role_a) {
+                if (s.ring && row >= (unsigned)s.ring) {
+                    if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
+                    __syncthreads();
+                }
+            } else {
+                if (threadIdx.x == 0) spin_until(s.a_done + row, (unsigned)s.tiles_a);
                 __syncthreads();
             }
-            pass_first_tile<T, LG_N1, LG_E1, LPB_A, FWD>(a, (long long)row * s.tiles_a + r, smem_raw);
-        } else {
-            if (threadIdx.x == 0) spin_until(s.a_done + row, (unsigned)s.tiles_a);
-            __syncthreads();
-            pass_second_tile<T, LG_N2, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw);
         }
+        auto peek_next = [&]() {
+            if (threadIdx.x == 0 && next < total) {
+                unsigned nrow, nr;
+                bool na;
+                decode_ticket(s, next, na, nrow, nr);
+                if (!na) { flag = *(const volatile unsigned *)(s.a_done + nrow); target = (unsigned)s.tiles_a; }
+                else if (s.ring && nrow >= (unsigned)s.ring) {
+                    flag = *(const volatile unsigned *)(s.b_done + (nrow - s.ring)); target = (unsigned)s.tiles_b;
+                }
+            }
+        };
+        if (role_a) pass_first_tile<T, LG_N1, LG_E1, LPB_A, FWD>(a, (long long)row * s.tiles_a + r, smem_raw, peek_next);
+        else pass_second_tile<T, LG_N2, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw, peek_next);
+        if (threadIdx.x == 0) { next_ticket_s = next; next_ready_s = flag >= target; }
         __syncthreads();          // every store of the tile is issued; shared memory is free again
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd((role_a ? s.a_done : s.b_done) + row, 1u);
-            ticket_s = next;
         }
-        __syncthreads();
-        ticket = ticket_s;
     }
 }
 
