@@ -103,12 +103,10 @@ template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_thread
 FusedEntry make_fused() {
     constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
-    constexpr int SM_A = LPB_A * Sched<LG_N1, LG_E1>::line_stride(LPB_A, (int)sizeof(cx<T>));
-    constexpr int SM_B = LPB_B * Sched<LG_N2, LG_E2>::line_stride(LPB_B, (int)sizeof(cx<T>));
     FusedEntry e;
     e.fn = four_step_fused<T, LG_N1, LG_N2, THREADS, FWD>;
     e.lg_n1 = LG_N1; e.lg_n2 = LG_N2; e.threads = THREADS; e.lpb_a = LPB_A; e.lpb_b = LPB_B;
-    e.smem = ((SM_A + LPB_A * (1 << LG_E1)) > SM_B ? (SM_A + LPB_A * (1 << LG_E1)) : SM_B) * (int)sizeof(cx<T>);   // + W^(q TT c) tables
+    e.smem = fused_smem_bytes<T, LG_N1, LG_N2, THREADS>();
     e.grid = 0;
     e.configured = false;
     return e;

@@ -130,14 +130,19 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
     static constexpr int LG_NS = S * LG_E, NS = 1 << LG_NS;
     static constexpr bool LAST = (S == Sc::STAGES - 1);
 
+    struct NoHook { DSC_DEV void operator()() const {} };
     static DSC_DEV void run(V (&v)[E], V *sm, const int t, const FftArgs &a, const LineSync &ls) {
-        run(v, sm, t, sm, t, a, ls);
+        run(v, sm, t, sm, t, a, ls, NoHook{});
     }
     // (sm_r, t_r): the line buffer and position this thread continues with AFTER this stage's exchange.  The
     // exchange is a free permutation point: a thread may come back as a different (line, position) of the
     // block -- the four-step second pass reads contiguous rows one line per warp and writes with adjacent
     // lanes on adjacent lines.  Needs a block-wide barrier when the two differ.
-    static DSC_DEV void run(V (&v)[E], V *sm, const int t, V *sm_r, const int t_r, const FftArgs &a, const LineSync &ls) {
+    // before_scatter(): called once, after this stage's butterflies and before its first write to shared memory
+    // (the persistent four-step kernel puts its "line buffers are free again" barrier there).
+    template <typename Hook>
+    static DSC_DEV void run(V (&v)[E], V *sm, const int t, V *sm_r, const int t_r, const FftArgs &a, const LineSync &ls,
+                            Hook &&before_scatter) {
         const V *__restrict__ tw = (const V *)a.tw[S];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -155,6 +160,7 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
 #pragma unroll
                 for (int p = 0; p < R; ++p) v[b + p * NB] = r[p];
             } else {
+                if (b == 0) before_scatter();
                 // scatter to (j-k)*R + k + p*NS; p*NS is a multiple of E past the first stage, so its
                 // padding is a constant too
                 const int base = ((j - k) << LG_R) + k;
@@ -173,7 +179,7 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = sm_r[Sc::pad_read(t_r, pt, c)];
             if constexpr (S + 1 < Sc::STAGES - 1) line_sync(ls);     // the next stage scatters into the same buffer
-            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm_r, t_r, sm_r, t_r, a, ls);
+            Stage<T, LG_N, LG_E, FWD, S + 1>::run(v, sm_r, t_r, sm_r, t_r, a, ls, NoHook{});
         }
     }
 };
@@ -622,80 +628,100 @@ fft_lines(const FftArgs a) {
 // The inter-pass twiddle W_n^(q k1), k1 = j + c*TT, is W^(q j) (one two-table lookup per thread) times
 // W^(q TT c), which depends on (line, c) only: L*E values per tile, built by the block into shared memory
 // once and read back as broadcasts.
-template <typename T, int LG_N, int LG_E, int L, bool FWD, typename Hook>
-DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, unsigned char *smem_raw, Hook &&loads_in_flight) {
+// Shared memory of a block: the line buffers (of whichever pass needs more), then -- at TABLE_AT elements -- two
+// copies of the first pass's (line, c) twiddle table that alternate from tile to tile (a block starts its
+// next tile while slower warps still finish the previous one, whichever pass that was).
+template <typename T, int LG_N, int LG_E, int L> struct PassTile {
+    using Sc = Sched<LG_N, LG_E>;
+    static constexpr int LINE = Sc::line_stride(L, (int)sizeof(cx<T>));
+    static constexpr int LINES = L * LINE;                 // elements
+    static constexpr int TABLE = L * Sc::E;                // elements per twiddle table copy
+};
+
+// LG_M: log2 of the OTHER factor (n = 2^(LG_N + LG_M)); with it the element strides of the dense case are
+// compile-time constants and the 2E accesses of a thread use one base pointer plus immediate offsets.
+template <typename T, int LG_N, int LG_M, int LG_E, int L, int TABLE_AT, bool FWD, typename Hook>
+DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, const int parity, unsigned char *smem_raw,
+                             Hook &&before_scatter) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
+    using PT = PassTile<T, LG_N, LG_E, L>;
     constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
     static_assert(Sc::STAGES >= 2, "the inter-pass table is published by the first exchange barrier");
-    constexpr int LINE = Sc::line_stride(L, (int)sizeof(V));
+    constexpr int LINE = PT::LINE;
+    constexpr long long STEP = (long long)TT << LG_M;     // elements between a thread's consecutive points
     V *sm_all = (V *)smem_raw;
     const int tid = threadIdx.x, l = tid % L, j = tid / L;
     V *sm = sm_all + l * LINE;
-    V *tw_c = sm_all + L * LINE;                      // [c][l]
+    static_assert(TABLE_AT >= PT::LINES, "twiddle tables overlap the line buffers");
+    V *tw_c = sm_all + TABLE_AT + parity * PT::TABLE;     // [c][l]
     const LineSync ls{SYNC_BLOCK, 0, THREADS};
 
     const long long line0 = tile * L;
-    const long long row = line0 >> a.inner_shift;
-    const unsigned q0 = (unsigned)(line0 & ((1LL << a.inner_shift) - 1)), q = q0 + (unsigned)l;
+    const long long row = line0 >> LG_M;
+    const unsigned q0 = (unsigned)(line0 & ((1LL << LG_M) - 1)), q = q0 + (unsigned)l;
+    const long long row_in = a.ring_in ? row % a.ring_in : row;
+    const long long row_out = a.ring_out ? row % a.ring_out : row;
+
+    V v[E];
+    if (a.in_kind == IN_COMPLEX && a.no_limit) {
+        // dense complex rows: element (m, q) of the row at m * 2^LG_M + q
+        const V *__restrict__ src = (const V *)a.x + row_in * a.gi.ostride + (((long long)j << LG_M) + q);
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = ld_stream(src + c * STEP);
+    } else {
+        const long long sbase = row_in * a.gi.ostride + (long long)q * a.gi.lstride + (long long)j * a.gi.estride;
+        const long long istep = (long long)TT * a.gi.estride;
+        const long long tlim = a.in_limit - (long long)q * a.gi.lstride - (long long)j * a.gi.estride;
+        if (a.in_kind == IN_COMPLEX) {
+            const V *__restrict__ src = (const V *)a.x + sbase;
+            const V zero = mk<T>((T)0, (T)0);
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = c * istep < tlim ? __ldcs(src + c * istep) : zero;
+        } else if (a.in_kind == IN_REAL) {
+            const T *__restrict__ src = (const T *)a.x + sbase;
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = mk<T>(c * istep < tlim ? __ldcs(src + c * istep) : (T)0, (T)0);
+        } else {  // IN_PAIRS
+            const T *__restrict__ src = (const T *)a.x + sbase;
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const T re = c * istep < tlim ? __ldcs(src + c * istep) : (T)0;
+                const T im = c * istep + a.gi_pstride < tlim ? __ldcs(src + c * istep + a.gi_pstride) : (T)0;
+                v[c] = mk<T>(re, im);
+            }
+        }
+    }
+    // the table lookups travel while the payload does
+    V w0 = mk<T>((T)1, (T)0);
     if (a.four_shift) {
         for (int i = tid; i < L * E; i += THREADS) {
             const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
             tw_c[i] = four_step_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
         }
-    }
-    const long long row_in = a.ring_in ? row % a.ring_in : row;
-    const long long row_out = a.ring_out ? row % a.ring_out : row;
-    const long long sbase = row_in * a.gi.ostride + (long long)q * a.gi.lstride + (long long)j * a.gi.estride;
-    const long long istep = (long long)TT * a.gi.estride;
-    const long long tlim = a.in_limit - (long long)q * a.gi.lstride - (long long)j * a.gi.estride;
-
-    V v[E];
-    if (a.in_kind == IN_COMPLEX) {
-        const V *__restrict__ src = (const V *)a.x + sbase;
-        if (a.no_limit) {
-#pragma unroll
-            for (int c = 0; c < E; ++c) v[c] = __ldcs(src + c * istep);
-        } else {
-            const V zero = mk<T>((T)0, (T)0);
-#pragma unroll
-            for (int c = 0; c < E; ++c) v[c] = c * istep < tlim ? __ldcs(src + c * istep) : zero;
-        }
-    } else if (a.in_kind == IN_REAL) {
-        const T *__restrict__ src = (const T *)a.x + sbase;
-#pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = mk<T>(c * istep < tlim ? __ldcs(src + c * istep) : (T)0, (T)0);
-    } else {  // IN_PAIRS
-        const T *__restrict__ src = (const T *)a.x + sbase;
-#pragma unroll
-        for (int c = 0; c < E; ++c) {
-            const T re = c * istep < tlim ? __ldcs(src + c * istep) : (T)0;
-            const T im = c * istep + a.gi_pstride < tlim ? __ldcs(src + c * istep + a.gi_pstride) : (T)0;
-            v[c] = mk<T>(re, im);
-        }
+        w0 = four_step_twiddle<T>(a, q * (unsigned)j);
     }
 
-    loads_in_flight();
-    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, j, a, ls);
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, j, sm, j, a, ls, before_scatter);
 
     if (a.four_shift) {
-        const V w0 = four_step_twiddle<T>(a, q * (unsigned)j);
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], c == 0 ? w0 : cmul(w0, tw_c[c * L + l]));
     }
-    V *__restrict__ op = (V *)a.out + row_out * a.go.ostride + (long long)q * a.go.lstride + (long long)j * a.go.estride;
-    const long long ostep = (long long)TT * a.go.estride;
+    // work row [k1][n2]: stays in L2 for the second pass
+    V *__restrict__ op = (V *)a.out + row_out * a.go.ostride + (((long long)j << LG_M) + q);
 #pragma unroll
-    for (int c = 0; c < E; ++c) op[c * ostep] = v[c];          // stays in L2 for the second pass
+    for (int c = 0; c < E; ++c) op[c * STEP] = v[c];
 }
 
-template <typename T, int LG_N, int LG_E, int L, bool FWD, typename Hook>
-DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned char *smem_raw, Hook &&loads_in_flight) {
+template <typename T, int LG_N, int LG_M, int LG_E, int L, bool FWD, typename Hook>
+DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned char *smem_raw, Hook &&before_scatter) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
     constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
     static_assert(Sc::STAGES >= 2, "the threads change lines at the first exchange");
-    constexpr int LINE = Sc::line_stride(L, (int)sizeof(V));
+    constexpr int LINE = PassTile<T, LG_N, LG_E, L>::LINE;
+    constexpr long long STEP = (long long)TT << LG_M;
     V *sm_all = (V *)smem_raw;
     const int tid = threadIdx.x;
     const int l1 = tid / TT, j1 = tid % TT;           // while loading: one line per TT consecutive threads
@@ -703,28 +729,28 @@ DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned c
     const LineSync ls{SYNC_BLOCK, 0, THREADS};
 
     const long long line0 = tile * L;
-    const long long row = line0 >> b.inner_shift;
-    const long long k0 = line0 & ((1LL << b.inner_shift) - 1);
+    const long long row = line0 >> LG_M;
+    const long long k0 = line0 & ((1LL << LG_M) - 1);
     const long long row_in = b.ring_in ? row % b.ring_in : row;
     const long long row_out = b.ring_out ? row % b.ring_out : row;
 
     V v[E];
-    const V *__restrict__ src = (const V *)b.x + row_in * b.gi.ostride + (k0 + l1) * b.gi.lstride + j1;
+    // work row [k1][n2], line k1 contiguous; written a moment ago by other SMs: L2 loads
+    const V *__restrict__ src = (const V *)b.x + row_in * b.gi.ostride + (((k0 + l1) << LG_N) + j1);
 #pragma unroll
-    for (int c = 0; c < E; ++c) v[c] = __ldcg(src + c * TT);      // written a moment ago by other SMs: L2 loads
+    for (int c = 0; c < E; ++c) v[c] = __ldcg(src + c * TT);
 
-    loads_in_flight();
-    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm_all + l1 * LINE, j1, sm_all + l2 * LINE, j2, b, ls);
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm_all + l1 * LINE, j1, sm_all + l2 * LINE, j2, b, ls, before_scatter);
 
     if (b.do_scale) {
         const T s = (T)b.scale;
 #pragma unroll
         for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
     }
-    V *__restrict__ op = (V *)b.out + row_out * b.go.ostride + (k0 + l2) * b.go.lstride + (long long)j2 * b.go.estride;
-    const long long ostep = (long long)TT * b.go.estride;
+    // X[k1 + n1 k2]
+    V *__restrict__ op = (V *)b.out + row_out * b.go.ostride + (((long long)j2 << LG_M) + (k0 + l2));
 #pragma unroll
-    for (int c = 0; c < E; ++c) __stcs(op + c * ostep, v[c]);
+    for (int c = 0; c < E; ++c) __stcs(op + c * STEP, v[c]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -782,13 +808,30 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
     __threadfence();
 }
 
+// shared-memory layout of the fused launch (elements): [ line buffers, max over the passes | 2 twiddle tables ]
+template <typename T, int LG_N1, int LG_N2, int THREADS> __host__ __device__ constexpr int fused_table_at() {
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+    constexpr int A = PassTile<T, LG_N1, LG_E1, (THREADS >> (LG_N1 - LG_E1))>::LINES;
+    constexpr int B = PassTile<T, LG_N2, LG_E2, (THREADS >> (LG_N2 - LG_E2))>::LINES;
+    return A > B ? A : B;
+}
+template <typename T, int LG_N1, int LG_N2, int THREADS> __host__ __device__ constexpr int fused_smem_bytes() {
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2);
+    return (fused_table_at<T, LG_N1, LG_N2, THREADS>() +
+            2 * PassTile<T, LG_N1, LG_E1, (THREADS >> (LG_N1 - LG_E1))>::TABLE) * (int)sizeof(cx<T>);
+}
+
 // Persistent blocks (the grid is what fits on the GPU at once): a block keeps taking tickets until none is
-// left.  Everything per tile that is not payload is taken off the block's critical path by thread 0:
-//   * the NEXT ticket is requested before the current tile starts;
-//   * once the current tile's payload loads are in flight, the dependency flag of the next tile is read, so
-//     that (with the ticket lag it is almost always already satisfied) the next tile starts without a poll;
-//   * the release of the finished tile (fence + counter) happens AFTER the barrier that ends the tile, while
-//     the other warps are already loading the next one.
+// left.  Per tile there are two block barriers, back to back around the scatter of the exchange: W ("every
+// warp is done with the line buffers of the previous tile") and E (the exchange itself).  There is no
+// barrier at the end of a tile: a warp that has stored its outputs goes straight on to load the next tile.
+// Everything per tile that is not payload is done by thread 0 off the critical path:
+//   * tickets are requested two tiles ahead; the ticket and readiness of tile i+1 are published in shared
+//     memory before W of tile i;
+//   * the dependency flag of tile i+1 is read at the start of tile i (with the ticket lag it is almost
+//     always already satisfied, and then tile i+1 starts without a poll);
+//   * tile i is released (release-add on its row counter) after W of tile i+1 -- by then every warp has
+//     issued its stores of tile i long ago.
 // A flag observed satisfied is followed by a block barrier and then by L2 (.cg) loads of the dependent data,
 // which the producer made visible at L2 before it incremented the flag.
 template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
@@ -797,32 +840,26 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
     constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
     static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
+    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS>();
     DSC_DYN_SMEM(smem_raw);
-    __shared__ unsigned next_ticket_s, next_ready_s;
+    __shared__ unsigned ctl_s[2][2];                   // [parity]{ticket, dependency already satisfied}
     const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
-    if (threadIdx.x == 0) { next_ticket_s = atomicAdd(s.ticket, 1u); next_ready_s = 0; }
+    unsigned pending = 0;                              // thread 0: ticket of the tile after the next one
+    if (threadIdx.x == 0) {
+        ctl_s[0][0] = atomicAdd(s.ticket, 1u);
+        ctl_s[0][1] = 0;
+        pending = atomicAdd(s.ticket, 1u);
+    }
     __syncthreads();
-    while (true) {
-        const unsigned ticket = next_ticket_s, ready = next_ready_s;
+    unsigned *prev_done = nullptr;                     // row counter of the previous tile, not yet released
+    for (int par = 0;; par ^= 1) {
+        const unsigned ticket = ctl_s[par][0], ready = ctl_s[par][1];
         if (ticket >= total) break;
         unsigned next = 0, flag = 0, target = 0;
-        if (threadIdx.x == 0) next = atomicAdd(s.ticket, 1u);
-        unsigned row, r;
-        bool role_a;
-        decode_ticket(s, ticket, role_a, row, r);
-        if (!ready) {
-            if (role_a) {
-                if (s.ring && row >= (unsigned)s.ring) {
-                    if (threadIdx.x == 0) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
-                    __syncthreads();
-                }
-            } else {
-                if (threadIdx.x == 0) spin_until(s.a_done + row, (unsigned)s.tiles_a);
-                __syncthreads();
-            }
-        }
-        auto peek_next = [&]() {
-            if (threadIdx.x == 0 && next < total) {
+        if (threadIdx.x == 0) {
+            next = pending;
+            pending = atomicAdd(s.ticket, 1u);
+            if (next < total) {
                 unsigned nrow, nr;
                 bool na;
                 decode_ticket(s, next, na, nrow, nr);
@@ -831,16 +868,32 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
                     flag = *(const volatile unsigned *)(s.b_done + (nrow - s.ring)); target = (unsigned)s.tiles_b;
                 }
             }
-        };
-        if (role_a) pass_first_tile<T, LG_N1, LG_E1, LPB_A, FWD>(a, (long long)row * s.tiles_a + r, smem_raw, peek_next);
-        else pass_second_tile<T, LG_N2, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw, peek_next);
-        if (threadIdx.x == 0) { next_ticket_s = next; next_ready_s = flag >= target; }
-        __syncthreads();          // every store of the tile is issued; shared memory is free again
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd((role_a ? s.a_done : s.b_done) + row, 1u);
         }
+        unsigned row, r;
+        bool role_a;
+        decode_ticket(s, ticket, role_a, row, r);
+        if (!ready) {
+            // about to wait for other tiles: release our own previous tile first (the awaited one may be it)
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (prev_done != nullptr) dsc_signal_release(prev_done);
+                if (!role_a) spin_until(s.a_done + row, (unsigned)s.tiles_a);
+                else if (s.ring && row >= (unsigned)s.ring) spin_until(s.b_done + (row - s.ring), (unsigned)s.tiles_b);
+            }
+            prev_done = nullptr;
+            __syncthreads();
+        }
+        auto before_scatter = [&]() {
+            if (threadIdx.x == 0) { ctl_s[par ^ 1][0] = next; ctl_s[par ^ 1][1] = flag >= target; }
+            __syncthreads();                                                          // W
+            if (threadIdx.x == 0 && prev_done != nullptr) dsc_signal_release(prev_done);
+        };
+        if (role_a) pass_first_tile<T, LG_N1, LG_N2, LG_E1, LPB_A, TABLE_AT, FWD>(a, (long long)row * s.tiles_a + r, par, smem_raw, before_scatter);
+        else pass_second_tile<T, LG_N2, LG_N1, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw, before_scatter);
+        prev_done = (role_a ? s.a_done : s.b_done) + row;
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && prev_done != nullptr) dsc_signal_release(prev_done);
 }
 
 // Large packed-real transforms (order N beyond one shared-memory pass): the same bin-pair

@@ -262,11 +262,12 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         s.tiles_b = (int)(n1 / fe->lpb_b);
         s.ring = (int)ring;
         s.rows = (int)rows;
-        // lag (in rows) between a row's first and second pass in ticket order: about two grids' worth of
-        // resident blocks, so second-pass blocks start on rows that are already complete; below the ring
+        // lag (in rows) between a row's first and second pass in ticket order: about three grids' worth of
+        // resident blocks (a tile is released half a tile after it ends and looked up a tile before it is
+        // needed), so second-pass blocks start on rows that are already complete; below the ring
         {
             const long long resident = fe->grid;
-            long long lag = (2 * resident + s.tiles_a + s.tiles_b - 1) / (s.tiles_a + s.tiles_b);
+            long long lag = (3 * resident + s.tiles_a + s.tiles_b - 1) / (s.tiles_a + s.tiles_b);
             if (lag < 1) lag = 1;
             // ... and at most half the ring, so a first-pass block that reuses a work row finds the
             // second pass of its previous owner long finished instead of spinning on it

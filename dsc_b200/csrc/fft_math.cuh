@@ -34,6 +34,17 @@ __device__ __forceinline__ void dsc_named_barrier(int id, int count) {
 __device__ __forceinline__ void dsc_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
+// counter += 1 with release semantics at GPU scope: orders the block's earlier writes (observed through a
+// block barrier) before the increment WITHOUT the L1 invalidation a full __threadfence() carries -- the
+// twiddle tables of a persistent block stay in L1 from tile to tile
+#if defined(DSC_EMUL)
+#define dsc_signal_release(p) ((void)atomicAdd((p), 1u))
+#else
+__device__ __forceinline__ void dsc_signal_release(unsigned *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
+}
+#endif
+
 // dynamic shared memory of the running block
 #if defined(DSC_EMUL)
 #define DSC_DYN_SMEM(name) unsigned char *name = dsc_emul::tls.smem
