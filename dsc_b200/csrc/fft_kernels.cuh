@@ -802,10 +802,18 @@ DSC_DEV void decode_ticket(const FourStepSync &s, unsigned ticket, bool &role_a,
     }
 }
 
+// Acquire load at GPU scope (no full memory barrier behind it, unlike volatile load + __threadfence()).
+#if defined(DSC_EMUL)
+DSC_DEV unsigned ld_acquire(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#else
+DSC_DEV unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#endif
 DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
-    const volatile unsigned *c = counter;
-    while (*c < target) __nanosleep(64);
-    __threadfence();
+    while (ld_acquire(counter) < target) __nanosleep(64);
 }
 
 // shared-memory layout of the fused launch (elements): [ line buffers, max over the passes | 2 twiddle tables ]
@@ -856,6 +864,7 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
         const unsigned ticket = ctl_s[par][0], ready = ctl_s[par][1];
         if (ticket >= total) break;
         unsigned next = 0, flag = 0, target = 0;
+        const unsigned *next_flag = nullptr;     // thread 0: the counter `flag` was read from
         if (threadIdx.x == 0) {
             next = pending;
             pending = atomicAdd(s.ticket, 1u);
@@ -863,10 +872,9 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
                 unsigned nrow, nr;
                 bool na;
                 decode_ticket(s, next, na, nrow, nr);
-                if (!na) { flag = *(const volatile unsigned *)(s.a_done + nrow); target = (unsigned)s.tiles_a; }
-                else if (s.ring && nrow >= (unsigned)s.ring) {
-                    flag = *(const volatile unsigned *)(s.b_done + (nrow - s.ring)); target = (unsigned)s.tiles_b;
-                }
+                if (!na) { next_flag = s.a_done + nrow; target = (unsigned)s.tiles_a; }
+                else if (s.ring && nrow >= (unsigned)s.ring) { next_flag = s.b_done + (nrow - s.ring); target = (unsigned)s.tiles_b; }
+                if (next_flag != nullptr) flag = *(const volatile unsigned *)next_flag;
             }
         }
         unsigned row, r;
@@ -884,7 +892,12 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
             __syncthreads();
         }
         auto before_scatter = [&]() {
-            if (threadIdx.x == 0) { ctl_s[par ^ 1][0] = next; ctl_s[par ^ 1][1] = flag >= target; }
+            if (threadIdx.x == 0) {
+                // not satisfied when this tile started?  look once more: a short wait here is far cheaper
+                // than the poll-and-barrier path at the start of the next tile
+                if (flag < target) flag = *(const volatile unsigned *)next_flag;
+                ctl_s[par ^ 1][0] = next; ctl_s[par ^ 1][1] = flag >= target;
+            }
             __syncthreads();                                                          // W
             if (threadIdx.x == 0 && prev_done != nullptr) dsc_signal_release(prev_done);
         };
