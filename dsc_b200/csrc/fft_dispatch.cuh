@@ -93,10 +93,12 @@ struct FusedEntry {
     bool configured;
 };
 
-// block size of the fused launch: 64 payload registers per thread, two blocks per SM
+// block size of the fused launch: 64 payload registers per thread, 512 threads per SM.  Two 256-thread blocks
+// overlap their phases better than one 512-thread block, except for float first passes of 1024 points, where
+// 256 threads are only 8 lines = 64-byte segments: there 16 lines (128-byte segments) win (measured +8 %).
 template <typename T> constexpr int fused_threads(int lg_n1, int lg_n2) {
-    (void)lg_n1; (void)lg_n2;
-    return 256;
+    (void)lg_n2;
+    return (sizeof(T) == 4 && lg_n1 >= 10) ? 512 : 256;
 }
 
 template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_threads<T>(LG_N1, LG_N2)>
