@@ -626,6 +626,7 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
     i64 rows_per_chunk = (i64) (chunk_bytes / DSC_MAX(DSC_MAX(in_row, out_row), (usize) 1));
     rows_per_chunk = DSC_MAX(rows_per_chunk, (i64) 1);
     if (j.outer * (i64) DSC_MAX(in_row, out_row) < (i64) (2 * chunk_bytes)) rows_per_chunk = j.outer;
+    if (x_on_device && !download) rows_per_chunk = j.outer;      // nothing crosses PCIe: nothing to overlap
 
     // work memory from the device scratch (two-pass intermediates, the filter's spectrum)
     ctx->dev_scratch.reset();

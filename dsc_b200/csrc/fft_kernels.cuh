@@ -78,6 +78,8 @@ struct FftArgs {
     long long ring_out;
     double scale;         // applied to the outputs when do_scale (1/N of the inverse)
     int do_scale;
+    int keep_out;         // four-step second pass: 1 = a later kernel re-reads the output soon (plain stores, the
+                          // rows stay in L2); 0 = streaming stores
 };
 
 template <int LG_N, int LG_E> struct Sched {
@@ -633,9 +635,22 @@ fft_lines(const FftArgs a) {
 // next tile while slower warps still finish the previous one, whichever pass that was).
 template <typename T, int LG_N, int LG_E, int L> struct PassTile {
     using Sc = Sched<LG_N, LG_E>;
-    static constexpr int LINE = Sc::line_stride(L, (int)sizeof(cx<T>));
-    static constexpr int LINES = L * LINE;                 // elements
-    static constexpr int TABLE = L * Sc::E;                // elements per twiddle table copy
+    // A bank phase is 128 bytes: PHASE lanes of one access.  Line l starts at l * LINE + rot(l), LINE a multiple
+    // of PHASE and rot = the bit reversal of l mod PHASE.  Whatever power-of-two group of lines shares a phase
+    // -- 16 adjacent lines at one position (adjacent lanes on adjacent lines), 8 lines x 2 positions, or the
+    // 2 / 4 adjacent short lines a half-warp spans while a second-pass tile loads -- the rotations of the
+    // group are an arithmetic progression that interleaves exactly with the positions (which advance by one
+    // element, or by E + 1 = 1 mod PHASE), so every exchange of the tile is conflict-free.
+    static constexpr int PHASE = 128 / (int)sizeof(cx<T>);
+    static constexpr int LINE = ((Sc::N + (Sc::N >> LG_E)) + 2 * PHASE - 2) / PHASE * PHASE;   // padded line + largest rotation
+    static constexpr int LINES = L * LINE;                  // elements
+    static constexpr int TABLE = L * Sc::E;                 // elements per twiddle table copy
+    static DSC_DEV int line_base(int l) {
+        int r = 0;
+#pragma unroll
+        for (int b = 1, m = PHASE >> 1; b < PHASE; b <<= 1, m >>= 1) if (l & b) r |= m;
+        return l * LINE + r;
+    }
 };
 
 // LG_M: log2 of the OTHER factor (n = 2^(LG_N + LG_M)); with it the element strides of the dense case are
@@ -648,11 +663,10 @@ DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, const int p
     using PT = PassTile<T, LG_N, LG_E, L>;
     constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
     static_assert(Sc::STAGES >= 2, "the inter-pass table is published by the first exchange barrier");
-    constexpr int LINE = PT::LINE;
     constexpr long long STEP = (long long)TT << LG_M;     // elements between a thread's consecutive points
     V *sm_all = (V *)smem_raw;
     const int tid = threadIdx.x, l = tid % L, j = tid / L;
-    V *sm = sm_all + l * LINE;
+    V *sm = sm_all + PT::line_base(l);
     static_assert(TABLE_AT >= PT::LINES, "twiddle tables overlap the line buffers");
     V *tw_c = sm_all + TABLE_AT + parity * PT::TABLE;     // [c][l]
     const LineSync ls{SYNC_BLOCK, 0, THREADS};
@@ -720,7 +734,7 @@ DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned c
     using V = cx<T>;
     constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
     static_assert(Sc::STAGES >= 2, "the threads change lines at the first exchange");
-    constexpr int LINE = PassTile<T, LG_N, LG_E, L>::LINE;
+    using PT = PassTile<T, LG_N, LG_E, L>;
     constexpr long long STEP = (long long)TT << LG_M;
     V *sm_all = (V *)smem_raw;
     const int tid = threadIdx.x;
@@ -740,7 +754,7 @@ DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned c
 #pragma unroll
     for (int c = 0; c < E; ++c) v[c] = __ldcg(src + c * TT);
 
-    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm_all + l1 * LINE, j1, sm_all + l2 * LINE, j2, b, ls, before_scatter);
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm_all + PT::line_base(l1), j1, sm_all + PT::line_base(l2), j2, b, ls, before_scatter);
 
     if (b.do_scale) {
         const T s = (T)b.scale;
@@ -749,8 +763,13 @@ DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned c
     }
     // X[k1 + n1 k2]
     V *__restrict__ op = (V *)b.out + row_out * b.go.ostride + (((long long)j2 << LG_M) + (k0 + l2));
+    if (b.keep_out) {
 #pragma unroll
-    for (int c = 0; c < E; ++c) __stcs(op + c * STEP, v[c]);
+        for (int c = 0; c < E; ++c) op[c * STEP] = v[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < E; ++c) __stcs(op + c * STEP, v[c]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 //
 // No cudaMalloc / cudaFree anywhere in this file: plan and work memory belong to the caller.
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 
@@ -189,6 +190,20 @@ inline int pow2_shift(long long v) {
     return s;
 }
 
+// Rows per pass of a multi-kernel pipeline.  Chunks small enough for the intermediate to stay in L2 between
+// the kernels (knob DSC_L2_CHUNK_BYTES) were measured SLOWER on B200 than whole-batch launches: the passes are
+// not HBM-bound, and short persistent launches lose more in ramp-up and tail than the L2 hits save
+// (config 3: 16/32/64 MiB chunks 11.3/7.3/5.8 ms against 5.4 ms unchunked).  Default: no cap.
+inline long long l2_chunk_rows(size_t row_bytes) {
+    static const size_t budget = [] {
+        const char *e = getenv("DSC_L2_CHUNK_BYTES");
+        const long long v = e ? atoll(e) : 0;
+        return v > 0 ? (size_t)v : (size_t)1 << 40;
+    }();
+    const long long r = (long long)(budget / (row_bytes ? row_bytes : 1));
+    return r > 1 ? r : 1;
+}
+
 inline size_t in_elem_size(const FftArgs &a, size_t real_size) {
     return (a.in_kind == IN_REAL || a.in_kind == IN_PAIRS) ? real_size : 2 * real_size;
 }
@@ -201,11 +216,18 @@ inline size_t in_elem_size(const FftArgs &a, size_t real_size) {
 // fused kernel does not cover fall back to two launches per chunk of rows.
 template <typename T, bool FWD>
 int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work, size_t work_bytes,
-              void *dst, long long dst_row_stride, bool scale, void *stream) {
+              void *dst, long long dst_row_stride, bool scale, void *stream, bool keep_out = false) {
     using V = cx<T>;
     const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
     const size_t row_bytes = (size_t)n * sizeof(V);
     if (rows <= 0) return 0;
+    // adjacent real pairs in full, aligned rows ARE dense complex rows: take the bandwidth path
+    if (first.in_kind == IN_PAIRS && first.gi_pstride == 1 && first.gi.lstride == 2 && first.gi.estride == 2 * n2 &&
+        first.gi.ostride % 2 == 0 && first.in_limit >= 2 * n && (uintptr_t)first.x % sizeof(V) == 0) {
+        first.in_kind = IN_COMPLEX;
+        first.gi = LineGeom{first.gi.ostride / 2, 1, n2};
+        first.in_limit = n;
+    }
 
     FftArgs a = first;
     a.inner = n2;
@@ -225,6 +247,7 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
     set_stage_tables<T>(b, p->tw2);
     b.strided = 1;
     b.do_scale = scale; b.scale = 1.0 / (double)n;
+    b.keep_out = keep_out;
 
     FusedEntry *fe = fused_entry<T, FWD>(p->lg_n1, p->lg_n2);
     const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
@@ -377,15 +400,25 @@ int run_rfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, 
     a.gi_pstride = 1;
     a.in_limit = take;
     a.in_kind = IN_PAIRS;
-    int rc = four_step<T, true>(p, a, outer, work, work_bytes, out, n + 1, false, stream);
-    if (rc) return rc;
-    const long long items = outer * (n / 2);
-    const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
-    auto mix = real_mix_rows<true, T>;
-    DSC_LAUNCH(mix, blocks, 256, 0, stream, (const V *)nullptr, (V *)out, outer, (int)n,
-               (long long)0, 0, (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift,
-               (1 << p->real_shift) - 1);
-    return check_launch("real_mix_rows");
+    // in chunks of rows that stay in L2 between the transform and the un-mix, which then costs no HBM read
+    const long long chunk = l2_chunk_rows((size_t)(n + 1) * sizeof(V));
+    for (long long r0 = 0; r0 < outer; r0 += chunk) {
+        const long long rows = outer - r0 < chunk ? outer - r0 : chunk;
+        FftArgs ac = a;
+        ac.x = (const T *)x + (size_t)r0 * x_n;
+        V *oc = (V *)out + (size_t)r0 * (n + 1);
+        int rc = four_step<T, true>(p, ac, rows, work, work_bytes, oc, n + 1, false, stream, true);
+        if (rc) return rc;
+        const long long items = rows * (n / 2);
+        const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+        auto mix = real_mix_rows<true, T>;
+        DSC_LAUNCH(mix, blocks, 256, 0, stream, (const V *)nullptr, oc, rows, (int)n,
+                   (long long)0, 0, (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift,
+                   (1 << p->real_shift) - 1);
+        rc = check_launch("real_mix_rows");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 template <typename T>
@@ -414,6 +447,7 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
     const size_t row_bytes = (size_t)n * sizeof(V);
     if (!work || work_bytes < 2 * row_bytes + 4096) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
     long long chunk = (long long)((work_bytes / 2) / row_bytes);
+    if (chunk > l2_chunk_rows(row_bytes)) chunk = l2_chunk_rows(row_bytes);     // the packed rows stay in L2
     if (chunk > outer) chunk = outer;
     V *z = (V *)work;
     char *fs_work = (char *)work + align_up((size_t)chunk * row_bytes, 256);
@@ -465,6 +499,7 @@ int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void
     const size_t row_bytes = (size_t)n * sizeof(V);
     if (!work || work_bytes < 2 * row_bytes + 4096) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
     long long chunk = (long long)((work_bytes / 2) / row_bytes);
+    if (chunk > l2_chunk_rows(row_bytes)) chunk = l2_chunk_rows(row_bytes);     // the packed rows stay in L2
     if (chunk > outer) chunk = outer;
     V *z = (V *)work;
     char *fs_work = (char *)work + align_up((size_t)chunk * row_bytes, 256);
@@ -477,7 +512,7 @@ int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void
         a.gi_pstride = 1;
         a.in_limit = take;
         a.in_kind = IN_PAIRS;
-        int rc = four_step<T, true>(p, a, rows, fs_work, fs_bytes, z, n, false, stream);
+        int rc = four_step<T, true>(p, a, rows, fs_work, fs_bytes, z, n, false, stream, true);
         if (rc) return rc;
         const long long items = rows * (n / 2);
         const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
