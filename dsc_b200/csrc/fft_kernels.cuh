@@ -33,8 +33,6 @@ enum Mode : int {
     MODE_C2R = 2,   // irfft: N+1 bins -> 2N reals, mixing fused before the first stage
     MODE_FAST = 3,  // dense complex lines (inner == 1, no pad/crop, whole blocks): the bandwidth path --
                     // one base pointer per thread, immediate offsets, streaming cache hints
-    MODE_PASS_A = 4,  // MODE_C2C as the first pass of the fused four-step kernel (payload in, L2 out)
-    MODE_PASS_B = 5,  // MODE_C2C/IN_ROWS as its second pass (L2 in, payload out)
     MODE_FILTER = 6,  // rfft -> times a spectrum -> irfft in ONE kernel: the spectrum never leaves shared memory
 };
 
@@ -262,22 +260,18 @@ template <int POL, typename V> DSC_DEV void st_pol(V *p, const V v) {
 // Body of one thread block: LPB lines starting at line `block * LPB`.
 // THREADS = LPB * TT.  Dynamic shared memory: LPB * Sched::LINE * sizeof(cx<T>).
 template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
-DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned char *smem_raw,
-                            const long long prefetch_block = -1) {
+DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned char *smem_raw) {
     using Sc = Sched<LG_N, LG_E>;
     using V = cx<T>;
     constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, THREADS = LPB * TT;
     constexpr int PAIRS = E > 1 ? E / 2 : 1;   // bin pairs per thread in the real modes
-    constexpr bool IS_C2C = MODE == MODE_C2C || MODE == MODE_PASS_A || MODE == MODE_PASS_B;
-    // four-step passes: the payload streams through once, the intermediate is L2-to-L2 traffic
-    constexpr int POL_IN = MODE == MODE_PASS_A ? POL_STREAM : MODE == MODE_PASS_B ? POL_L2 : POL_DEFAULT;
-    constexpr int POL_OUT = MODE == MODE_PASS_B ? POL_STREAM : POL_DEFAULT;
+    constexpr bool IS_C2C = MODE == MODE_C2C;
+    constexpr int POL_IN = POL_DEFAULT, POL_OUT = POL_DEFAULT;
     V *sm_all = (V *)smem_raw;
 
-    constexpr bool TILED = MODE == MODE_PASS_A || MODE == MODE_PASS_B;   // cooperative tile staging
     const int tid = threadIdx.x;
     int l, t;
-    if (!TILED && a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
+    if (a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
     constexpr int LINE = Sc::line_stride(LPB, (int)sizeof(V), MODE == MODE_FAST ? TT : 0);
     V *sm = sm_all + l * LINE;
     // A line's exchanges need: a warp barrier when the line lives inside one warp; its own hardware
@@ -285,9 +279,8 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     // progress independently of each other); otherwise the block barrier.
     LineSync ls;
     ls.id = 1 + l; ls.count = TT;
-    if (!TILED && a.strided) ls.kind = SYNC_BLOCK;
+    if (a.strided) ls.kind = SYNC_BLOCK;
     else if (TT <= 32) ls.kind = SYNC_WARP;
-    else if (TILED && LPB <= 15 && TT % 32 == 0) ls.kind = SYNC_LINE;
     else ls.kind = SYNC_BLOCK;
 
     const long long line = block * LPB + l;
@@ -307,22 +300,6 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     // read iff offset < lim; "no limit" (dense lines) is encoded as a huge lim by the host
     const long long lim = active ? a.in_limit - in * a.gi.lstride : 0;
     const V zero = mk<T>((T)0, (T)0);
-    // PASS_A: per-line table W_M^(q * TT * c), c < E, behind the line buffers (visible after the tile-load barrier)
-    V *tw_c = sm_all + LPB * LINE;
-    if constexpr (MODE == MODE_PASS_A) {
-        if (a.four_shift)
-            for (int c = t; c < E; c += TT) tw_c[l * E + c] = four_step_twiddle<T>(a, (unsigned)in * (unsigned)(TT * c));
-    }
-    // cooperative tile copies (TILED): lane = line within the tile, then position; each thread moves E
-    // elements at positions p0 + c*TT of line lt.  The fused launch guarantees whole tiles inside one row.
-    const int lt = tid % LPB, p0 = tid / LPB;
-    long long tile_o = 0, tile_in0 = 0;
-    if constexpr (TILED) {
-        const long long line0 = block * LPB;
-        tile_o = line0 >> a.inner_shift;
-        tile_in0 = line0 & ((1LL << a.inner_shift) - 1);
-    }
-
     V v[E];
 
     // ---------------------------------------------------------------- load
@@ -348,55 +325,6 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
             for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
             __syncthreads();
         }
-    } else if constexpr (MODE == MODE_PASS_A) {
-        // strided source tile -> shared memory (adjacent lanes = adjacent lines = contiguous bytes)
-        const long long row_in = a.ring_in ? tile_o % a.ring_in : tile_o;
-        const long long sbase = row_in * a.gi.ostride + (tile_in0 + lt) * a.gi.lstride + (long long)p0 * a.gi.estride;
-        const long long tlim = a.in_limit - (tile_in0 + lt) * a.gi.lstride - (long long)p0 * a.gi.estride;
-        V *dst = sm_all + lt * LINE;
-        const int pp0 = Sc::pad(p0);
-        if (a.in_kind == IN_COMPLEX) {
-            const V *__restrict__ src = (const V *)a.x + sbase;
-#pragma unroll
-            for (int c = 0; c < E; ++c)
-                dst[Sc::pad_read(p0, pp0, c)] = (a.no_limit || c * istep < tlim) ? ld_pol<POL_IN>(src + c * istep) : zero;
-        } else if (a.in_kind == IN_REAL) {
-            const T *__restrict__ src = (const T *)a.x + sbase;
-#pragma unroll
-            for (int c = 0; c < E; ++c)
-                dst[Sc::pad_read(p0, pp0, c)] = mk<T>(c * istep < tlim ? ld_pol<POL_IN>(src + c * istep) : (T)0, (T)0);
-        } else {  // IN_PAIRS
-            const T *__restrict__ src = (const T *)a.x + sbase;
-#pragma unroll
-            for (int c = 0; c < E; ++c) {
-                const T re = c * istep < tlim ? ld_pol<POL_IN>(src + c * istep) : (T)0;
-                const T im = c * istep + a.gi_pstride < tlim ? ld_pol<POL_IN>(src + c * istep + a.gi_pstride) : (T)0;
-                dst[Sc::pad_read(p0, pp0, c)] = mk<T>(re, im);
-            }
-        }
-        if (prefetch_block >= 0) {
-            // pull the tile that a block will need a few hundred tickets from now into L2, so that its demand
-            // loads hit L2 instead of waiting for HBM (DRAM bandwidth is not the limit of this pass, latency is)
-            const long long f0 = prefetch_block * LPB;
-            const long long fo = f0 >> a.inner_shift, fin0 = f0 & ((1LL << a.inner_shift) - 1);
-            const long long fbase = fo * a.gi.ostride + (fin0 + lt) * a.gi.lstride + (long long)p0 * a.gi.estride;
-            const size_t es = a.in_kind == IN_COMPLEX ? sizeof(V) : sizeof(T);
-            const char *fp = (const char *)a.x + (size_t)fbase * es;
-            if (lt == 0 || es * (size_t)a.gi.lstride * LPB > 128) {     // one prefetch per segment is enough
-#pragma unroll
-                for (int c = 0; c < E; ++c) dsc_prefetch_l2(fp + (size_t)(c * istep) * es);
-            }
-        }
-        __syncthreads();
-        const int pt = Sc::pad(t);
-#pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
-        line_sync(ls);
-    } else if constexpr (MODE == MODE_PASS_B) {
-        // contiguous work rows straight into registers (written a moment ago by other SMs: L2 loads)
-        const V *__restrict__ xp = (const V *)a.x + ibase + t;
-#pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = ld_pol<POL_IN>(xp + c * TT);
     } else if constexpr (MODE == MODE_C2R) {
         // bins X[0..N] -> packed z[0..N); DC/Nyquist use real parts only (dsc_fft.h:227-228)
         const V *__restrict__ xc = (const V *)a.x + ibase;
@@ -528,29 +456,6 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
             V *__restrict__ ob = (V *)a.out + block * (long long)(LPB * N);
             for (int e = tid; e < LPB * N; e += THREADS) st_stream(ob + e, sm_all[(e / N) * LINE + Sc::pad(e % N)]);
         }
-    } else if constexpr (TILED) {
-        if (MODE == MODE_PASS_A && a.four_shift) {
-            // times W_M^(q k1), q = this line's column n2, k1 = t + c*TT:  W^(q t) * W^(q TT c).
-            // The first factor is one (two-table) lookup per thread; the second depends only on (line, c)
-            // and was put in shared memory by the line's first E threads at kernel start -- 16 broadcast
-            // LDS instead of 32 scattered global gathers per thread.
-            const V w0 = four_step_twiddle<T>(a, (unsigned)in * (unsigned)t);
-            const V *tc = tw_c + l * E;
-#pragma unroll
-            for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], c == 0 ? w0 : cmul(w0, tc[c]));
-        }
-        // registers -> shared memory (own line), then the block stores the tile with adjacent lanes on
-        // adjacent lines: contiguous LPB*sizeof(V) bytes per position
-        const int pt = Sc::pad(t);
-#pragma unroll
-        for (int c = 0; c < E; ++c) sm[Sc::pad_read(t, pt, c)] = v[c];
-        __syncthreads();
-        const long long row_out = a.ring_out ? tile_o % a.ring_out : tile_o;
-        V *__restrict__ op = (V *)a.out + row_out * a.go.ostride + (tile_in0 + lt) * a.go.lstride + (long long)p0 * a.go.estride;
-        const V *src = sm_all + lt * LINE;
-        const int pp0 = Sc::pad(p0);
-#pragma unroll
-        for (int c = 0; c < E; ++c) st_pol<POL_OUT>(op + c * ostep, src[Sc::pad_read(p0, pp0, c)]);
     } else if constexpr (IS_C2C) {
         if (a.four_shift) {   // four-step first pass: times W_M^(in * k1)
             const unsigned q = (unsigned)in;
@@ -775,16 +680,17 @@ DSC_DEV void pass_second_tile(const FftArgs &b, const long long tile, unsigned c
 // ------------------------------------------------------------------------------------------
 // Four-step transform n = n1*n2 as ONE launch.
 //
-// Per top-level line ("row") there are TA first-pass blocks (length-n1 transforms over stride-n2
-// data, times W_n^(n2 k1), into a ring of work rows) and TB second-pass blocks (length-n2 transforms
-// of contiguous work rows, stored with stride n1).  Blocks take a ticket when they start; ticket
-// order is row-major with a row's A blocks before its B blocks, so a block only ever waits for
-// blocks with SMALLER tickets, which are already running -- no deadlock whatever the dispatch
-// order.  A B block waits until all TA A blocks of its row have published; an A block that reuses a
-// ring slot waits until the B blocks of the row that last used it are done.  The intermediate of a
-// row is therefore consumed a few microseconds after it is produced and never leaves L2
-// (POL_L2 loads bypass the non-coherent L1; the payload itself streams with evict-first hints),
-// so HBM sees one read and one write per element although there are two passes.
+// Per top-level line ("row") there are TA first-pass tiles (length-n1 transforms over stride-n2
+// data, times W_n^(n2 k1), into a ring of work rows) and TB second-pass tiles (length-n2 transforms
+// of contiguous work rows, stored with stride n1).  Blocks take tickets; ticket order is row-major
+// with a row's first-pass tiles `lag` rows ahead of its second-pass tiles, so a tile only ever waits
+// for tiles with SMALLER tickets, which are done or being worked on -- no deadlock whatever the
+// dispatch order.  A second-pass tile needs all TA first-pass tiles of its row; a first-pass tile that
+// reuses a ring slot needs the second pass of the row that last used it.  The intermediate of a
+// row is therefore consumed a few microseconds after it is produced and never leaves L2 (.cg loads
+// bypass the non-coherent L1; the payload itself streams), so HBM sees one read and one write per
+// element although there are two passes.
+
 // points per thread of a four-step pass (must agree with lg_e_for in fft_dispatch.cuh for these lengths)
 template <typename T> __host__ __device__ constexpr int pass_lg_e(int lg_n, int lg_other) {
     // register-direct tiles: radix-32 (float) / radix-16 (double) register tiles, so that float lines of up to
@@ -801,7 +707,6 @@ struct FourStepSync {
     int tiles_a, tiles_b;
     int ring;            // work rows (0 = one work row per top-level row, no reuse)
     int rows;
-    int prefetch;        // a first-pass block prefetches (to L2) the tile of the block this many tickets ahead
     int lag;             // ticket order: the B blocks of row r come after the A blocks of row r + lag, so
                          // that in steady state a B block finds its row already complete and never spins
 };

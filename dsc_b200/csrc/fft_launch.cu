@@ -297,10 +297,6 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
             if (ring > 0 && lag > ring / 2) lag = ring / 2;
             if (lag > rows) lag = rows;
             s.lag = (int)lag;
-            // L2 prefetch of the first-pass tile `prefetch` tickets ahead: measured no gain on B200 (the pass is
-            // not waiting on DRAM latency), so it is off unless the knob asks for it
-            const char *pf = getenv("DSC_FUSED_PREFETCH");
-            s.prefetch = pf ? atoi(pf) : 0;
         }
         V *mid = (V *)((char *)work + sync_bytes);
         a.out = mid; a.lines = rows * n2; a.ring_out = ring; a.inner_shift = p->lg_n2;
