@@ -41,10 +41,12 @@ template <typename T> constexpr int lpb_c(int lg_n) {
     const int tt = 1 << (lg_n - lg_e_for<T>(lg_n));
     return imax(1, 256 / tt);
 }
-// lines per block, strided shape: enough adjacent lines for coalescing, at most 512 threads
+// lines per block, strided shape: enough adjacent lines for coalescing; at most 1024 threads with the
+// standard register tile (<= 64 registers per thread), 512 with the double-size tile of the longest lines
 template <typename T> constexpr int lpb_s(int lg_n) {
     const int tt = 1 << (lg_n - lg_e_for<T>(lg_n));
-    return imax(1, imin(imax(Tile<T>::COAL, 256 / tt), 512 / tt));
+    const int cap = lg_e_for<T>(lg_n) > Tile<T>::LG_E ? 512 : 1024;
+    return imax(1, imin(imax(Tile<T>::COAL, 256 / tt), cap / tt));
 }
 
 template <typename T, bool FWD, int MODE, bool SV, int LG_N>
