@@ -27,6 +27,10 @@
 
 namespace dscfft {
 
+#ifndef DSC_TW_LADDER
+#define DSC_TW_LADDER 1
+#endif
+
 enum Mode : int {
     MODE_C2C = 0,   // complex / real-cast / real-pair / staged-row input -> complex out
     MODE_R2C = 1,   // rfft : 2N reals -> N+1 bins, un-mixing fused after the last stage
@@ -152,8 +156,27 @@ template <typename T, int LG_N, int LG_E, bool FWD, int S> struct Stage {
 #pragma unroll
             for (int m = 0; m < R; ++m) r[m] = v[b + m * NB];
             if constexpr (S > 0) {
+                if constexpr (DSC_TW_LADDER && R >= 8 && sizeof(T) == 8) {
+                    // W^(k m) for all m from the log2(R) table rows m = 1, 2, 4, ...: w_m = w_hi(m) * w_(m - hi(m)).
+                    // At most log2(R) - 1 roundings deep; trades R - 1 - log2(R) loads (the load/store pipe is
+                    // the busiest unit of these kernels) for as many complex multiplies on the FP pipe.
+                    // Measured on B200: complex128 2^10 / 2^12 / 2^13 +6 / +11 / +4 % (16-byte twiddles are two
+                    // wavefronts per 16 lanes); complex64 within +-3 %, so float keeps the exact table values.
+                    V w[R];
 #pragma unroll
-                for (int m = 1; m < R; ++m) r[m] = cmul_tw<FWD>(r[m], __ldg(tw + (m - 1) * NS + k));
+                    for (int m = 1; m < R; ++m) {
+                        if ((m & (m - 1)) == 0) w[m] = __ldg(tw + (m - 1) * NS + k);
+                        else {
+                            int hi = 1;
+                            while (hi * 2 <= m) hi *= 2;
+                            w[m] = cmul(w[hi], w[m - hi]);
+                        }
+                        r[m] = cmul_tw<FWD>(r[m], w[m]);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 1; m < R; ++m) r[m] = cmul_tw<FWD>(r[m], __ldg(tw + (m - 1) * NS + k));
+                }
             }
             Dft<R, FWD, T>::run(r);
             if constexpr (LAST) {
