@@ -46,7 +46,10 @@ def test_golden_vectors(dev, i, meta, arrs):
     assert rel_l2(got, want) < TOL[want.dtype]      # north-star tolerance: 1e-5 / 1e-12
 
 
-@pytest.mark.parametrize("dtype,lg,rows", [("complex64", 20, 3), ("complex64", 18, 5), ("complex128", 17, 3),
+# the many-row cases wrap the ring of work rows of the persistent four-step launch several times
+@pytest.mark.parametrize("dtype,lg,rows", [("complex64", 20, 3), ("complex64", 19, 3), ("complex64", 18, 5),
+                                           ("complex64", 16, 9), ("complex64", 15, 1500), ("complex128", 19, 2),
+                                           ("complex128", 17, 3), ("complex128", 14, 1100),
                                            ("complex64", 12, 4096), ("complex128", 12, 513)])
 def test_large_vs_oracle(dev, dtype, lg, rows):
     rng = np.random.default_rng(lg)
