@@ -87,8 +87,14 @@ def _load():
         f.argtypes = [C.c_void_p, _TP, _TP, C.c_int, C.c_int]
     L.dsc_fft_filter.restype = _TP
     L.dsc_fft_filter.argtypes = [C.c_void_p, _TP, _TP, _TP, C.c_int, C.c_int]
-    L.dsc_mul.restype = _TP
-    L.dsc_mul.argtypes = [C.c_void_p, _TP, _TP, _TP]
+    for name in ("dsc_add", "dsc_sub", "dsc_mul", "dsc_div"):
+        getattr(L, name).restype = _TP
+        getattr(L, name).argtypes = [C.c_void_p, _TP, _TP, _TP]
+    L.dsc_abs.restype = _TP
+    L.dsc_abs.argtypes = [C.c_void_p, _TP, _TP]
+    for name in ("dsc_angle", "dsc_real", "dsc_imag", "dsc_conj"):
+        getattr(L, name).restype = _TP
+        getattr(L, name).argtypes = [C.c_void_p, _TP]
     L.dsc_tensor_get_slice.restype = _TP
     L.dsc_traces_record.argtypes = [C.c_void_p, C.c_bool]
     L.dsc_dump_traces.argtypes = [C.c_void_p, C.c_char_p]
@@ -96,6 +102,7 @@ def _load():
     L.dsc_cuda_set_residency.argtypes = [C.c_void_p, C.c_int]
     L.dsc_cuda_sync_host.argtypes = [C.c_void_p, _TP]
     L.dsc_cuda_touch_host.argtypes = [C.c_void_p, _TP]
+    L.dsc_cuda_prefetch.argtypes = [C.c_void_p, _TP]
     _lib = L
     return L
 
@@ -180,6 +187,15 @@ class Tensor:
     def __mul__(self, other: "Tensor") -> "Tensor":
         return mul(self, other)
 
+    def __add__(self, other: "Tensor") -> "Tensor":
+        return add(self, other)
+
+    def __sub__(self, other: "Tensor") -> "Tensor":
+        return sub(self, other)
+
+    def __truediv__(self, other: "Tensor") -> "Tensor":
+        return true_div(self, other)
+
     def __getitem__(self, item) -> "Tensor":
         items = item if isinstance(item, tuple) else (item,)
         args = []
@@ -233,10 +249,56 @@ def irfft(x, out: Optional[Tensor] = None, n: int = -1, axis: int = -1) -> Tenso
     return _xform("dsc_irfft", x, out, n, axis)
 
 
-def mul(a, b, out: Optional[Tensor] = None) -> Tensor:
+def _binary(name: str, a, b, out: Optional[Tensor]) -> Tensor:
     a, b = _as_tensor(a), _as_tensor(b)
-    res = _load().dsc_mul(_get_ctx(), a.c, b.c, out.c if out is not None else None)
+    res = getattr(_load(), name)(_get_ctx(), a.c, b.c, out.c if out is not None else None)
     return Tensor(res, view=out is not None)
+
+
+def add(a, b, out: Optional[Tensor] = None) -> Tensor:
+    return _binary("dsc_add", a, b, out)
+
+
+def sub(a, b, out: Optional[Tensor] = None) -> Tensor:
+    return _binary("dsc_sub", a, b, out)
+
+
+def mul(a, b, out: Optional[Tensor] = None) -> Tensor:
+    return _binary("dsc_mul", a, b, out)
+
+
+def true_div(a, b, out: Optional[Tensor] = None) -> Tensor:
+    return _binary("dsc_div", a, b, out)
+
+
+def abs(x, out: Optional[Tensor] = None) -> Tensor:   # noqa: A001 (the reference wrapper's name, python/dsc/tensor.py)
+    x = _as_tensor(x)
+    res = _load().dsc_abs(_get_ctx(), x.c, out.c if out is not None else None)
+    return Tensor(res, view=out is not None)
+
+
+def _unary_new(name: str, x) -> Tensor:
+    """Ops that may hand back their argument itself (real / conj of a real tensor, dsc.cpp:1549-1552)."""
+    x = _as_tensor(x)
+    res = getattr(_load(), name)(_get_ctx(), x.c)
+    same = C.cast(res, C.c_void_p).value == C.cast(x.c, C.c_void_p).value
+    return x if same else Tensor(res)
+
+
+def angle(x) -> Tensor:
+    return _unary_new("dsc_angle", x)
+
+
+def real(x) -> Tensor:
+    return _unary_new("dsc_real", x)
+
+
+def imag(x) -> Tensor:
+    return _unary_new("dsc_imag", x)
+
+
+def conj(x) -> Tensor:
+    return _unary_new("dsc_conj", x)
 
 
 def fft_filter(x, B, out: Optional[Tensor] = None, n: int = -1, axis: int = -1) -> Tensor:
@@ -265,6 +327,11 @@ def clear_traces() -> None:
 def set_residency(mode: int) -> None:
     """0 strict (default), 1 keep results on the device, 2 also defer downloads (include/dsc.h)."""
     _load().dsc_cuda_set_residency(_get_ctx(), int(mode))
+
+
+def prefetch(x: Tensor) -> None:
+    """Upload x to its device mirror now (residency >= 1), so that later ops on it run on the device."""
+    _load().dsc_cuda_prefetch(_get_ctx(), x.c)
 
 
 def sync_host(x: Tensor) -> None:

@@ -243,36 +243,21 @@ void dsc_host_needed(dsc_ctx *ctx, const dsc_tensor *x) noexcept {
     if (x != nullptr && (x->buffer->flags & DSC_BUF_HOST_STALE)) download_now(ctx, x->buffer);
 }
 
-bool dsc_try_device_cmul(dsc_ctx *ctx, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept {
-    // The spectrum product between rfft and irfft (dsc.cpp:1273-1284) without a round trip through the host:
-    // only taken when the data is already device-resident, so the default (strict) mode never gets here.
-    if (!ctx->has_device || ctx->residency < 1) return false;
-    if (xa->dtype != out->dtype || xb->dtype != out->dtype || (out->dtype != C32 && out->dtype != C64)) return false;
-    if (!((xa->buffer->flags | xb->buffer->flags) & DSC_BUF_DEV_VALID)) return false;
-    if (memcmp(xa->shape, out->shape, sizeof(out->shape)) != 0) return false;
-    const bool same = memcmp(xb->shape, out->shape, sizeof(out->shape)) == 0;
-    bool row = xb->shape[DSC_MAX_DIMS - 1] == out->shape[DSC_MAX_DIMS - 1];
-    for (int d = 0; d < DSC_MAX_DIMS - 1; ++d) row = row && xb->shape[d] == 1;
-    if (!same && !row) return false;
-    if (xa->buffer == out->buffer || xb->buffer == out->buffer) return false;
+namespace {
+// device pointer of an operand, uploading it first if only the host copy is current
+void *operand_on_device(dsc_ctx *ctx, const dsc_tensor *t) noexcept {
+    dsc_tensor_buffer *b = t->buffer;
+    b->busy = 1;
+    void *d = dsc_dev_ptr(ctx, b);
+    if (!(b->flags & DSC_BUF_DEV_VALID)) {
+        dscdev::copy_h2d(d, (byte *) b + BUFFER_HEADER, b->nbytes, 0);
+        b->flags |= DSC_BUF_DEV_VALID;
+    }
+    return d;
+}
 
-    auto on_device = [&](const dsc_tensor *t) -> void * {
-        dsc_tensor_buffer *b = t->buffer;
-        b->busy = 1;
-        void *d = dsc_dev_ptr(ctx, b);
-        if (!(b->flags & DSC_BUF_DEV_VALID)) {
-            dscdev::copy_h2d(d, (byte *) b + BUFFER_HEADER, b->nbytes, 0);
-            b->flags |= DSC_BUF_DEV_VALID;
-        }
-        return d;
-    };
-    const void *da = on_device(xa), *db = on_device(xb);
-    out->buffer->busy = 1;
-    void *dout = dsc_dev_ptr(ctx, out->buffer);
-    const i64 cols = out->shape[DSC_MAX_DIMS - 1];
-    const i64 rows = cols > 0 ? out->ne / cols : 0;
-    if (dsc_cuda_cmul(da, db, dout, out->dtype, rows, cols, same && rows > 1, dscdev::stream(0)) != 0)
-        DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+// the result of a device op: valid on the device; downloaded now unless the context downloads lazily
+void result_on_device(dsc_ctx *ctx, dsc_tensor *out, void *dout) noexcept {
     out->buffer->flags |= DSC_BUF_DEV_VALID;
     if (ctx->residency == 2) {
         out->buffer->flags |= DSC_BUF_HOST_STALE;
@@ -281,7 +266,48 @@ bool dsc_try_device_cmul(dsc_ctx *ctx, const dsc_tensor *xa, const dsc_tensor *x
         dscdev::copy_d2h((byte *) out->buffer + BUFFER_HEADER, dout, out->buffer->nbytes, 2);
         dscdev::stream_sync(2);
     }
+}
+}  // namespace
+
+bool dsc_try_device_binary(dsc_ctx *ctx, const int op, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept {
+    // Arithmetic between transforms (the spectrum product of dsc.cpp:1273-1284, gains, offsets, ratios) without a
+    // round trip through the host: only taken when an operand is already device-resident, so the default
+    // (strict) mode never gets here.  Same dtype everywhere; xb same shape, one row, or one element.
+    if (!ctx->has_device || ctx->residency < 1) return false;
+    if (xa->dtype != out->dtype || xb->dtype != out->dtype) return false;
+    if (!((xa->buffer->flags | xb->buffer->flags) & DSC_BUF_DEV_VALID)) return false;
+    if (memcmp(xa->shape, out->shape, sizeof(out->shape)) != 0) return false;
+    const bool same = memcmp(xb->shape, out->shape, sizeof(out->shape)) == 0;
+    bool row = xb->shape[DSC_MAX_DIMS - 1] == out->shape[DSC_MAX_DIMS - 1];
+    for (int d = 0; d < DSC_MAX_DIMS - 1; ++d) row = row && xb->shape[d] == 1;
+    const bool scalar = xb->ne == 1;
+    if (!same && !row && !scalar) return false;
+    if (xa->buffer == out->buffer || xb->buffer == out->buffer) return false;
+
+    const void *da = operand_on_device(ctx, xa), *db = operand_on_device(ctx, xb);
+    out->buffer->busy = 1;
+    void *dout = dsc_dev_ptr(ctx, out->buffer);
+    const i64 cols = out->shape[DSC_MAX_DIMS - 1];
+    const i64 rows = cols > 0 ? out->ne / cols : 0;
+    const int b_mode = same ? 1 : row ? 0 : 2;
+    if (dsc_cuda_binary(op, da, db, dout, out->dtype, rows, cols, b_mode, dscdev::stream(0)) != 0)
+        DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    result_on_device(ctx, out, dout);
     xa->buffer->busy = xb->buffer->busy = out->buffer->busy = 0;
+    return true;
+}
+
+bool dsc_try_device_unary(dsc_ctx *ctx, const int op, const dsc_tensor *x, dsc_tensor *out) noexcept {
+    // |X|, arg X, Re, Im, conj of a spectrum that lives on the device (dsc.cpp:1480-1622)
+    if (!ctx->has_device || ctx->residency < 1) return false;
+    if (x->dtype != C32 && x->dtype != C64) return false;
+    if (!(x->buffer->flags & DSC_BUF_DEV_VALID) || x->buffer == out->buffer) return false;
+    const void *dx = operand_on_device(ctx, x);
+    out->buffer->busy = 1;
+    void *dout = dsc_dev_ptr(ctx, out->buffer);
+    if (dsc_cuda_unary(op, dx, x->dtype, dout, x->ne, dscdev::stream(0)) != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    result_on_device(ctx, out, dout);
+    x->buffer->busy = out->buffer->busy = 0;
     return true;
 }
 
@@ -317,6 +343,13 @@ void dsc_cuda_set_residency(dsc_ctx *ctx, const int mode) noexcept {
 void dsc_cuda_sync_host(dsc_ctx *ctx, dsc_tensor *x) noexcept { dsc_host_needed(ctx, x); }
 
 void dsc_cuda_touch_host(dsc_ctx *, dsc_tensor *x) noexcept { if (x) dsc_host_written(x->buffer); }
+
+void dsc_cuda_prefetch(dsc_ctx *ctx, dsc_tensor *x) noexcept {
+    if (x == nullptr || !ctx->has_device || ctx->residency < 1 || x->buffer->nbytes == 0) return;
+    operand_on_device(ctx, x);
+    dscdev::stream_sync(0);          // the caller may overwrite the host payload right away
+    x->buffer->busy = 0;
+}
 
 // =============================================================================================
 // tensors

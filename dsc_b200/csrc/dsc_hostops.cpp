@@ -430,11 +430,12 @@ void dsc_tensor_set_slice(dsc_ctx *ctx, dsc_tensor *DSC_RESTRICT xa, const dsc_t
 
 namespace {
 
-struct op_add { template <typename T> T operator()(T a, T b) const noexcept { return a + b; } };
-struct op_sub { template <typename T> T operator()(T a, T b) const noexcept { return a - b; } };
-struct op_mul { template <typename T> T operator()(T a, T b) const noexcept { return a * b; } };
-struct op_div { template <typename T> T operator()(T a, T b) const noexcept { return a / b; } };
-struct op_pow { template <typename T> T operator()(T a, T b) const noexcept { return std::pow(a, b); } };
+// device_op: the launch layer's code of the operator, -1 = host only
+struct op_add { static constexpr int device_op = DSC_CUDA_OP_ADD; template <typename T> T operator()(T a, T b) const noexcept { return a + b; } };
+struct op_sub { static constexpr int device_op = DSC_CUDA_OP_SUB; template <typename T> T operator()(T a, T b) const noexcept { return a - b; } };
+struct op_mul { static constexpr int device_op = DSC_CUDA_OP_MUL; template <typename T> T operator()(T a, T b) const noexcept { return a * b; } };
+struct op_div { static constexpr int device_op = DSC_CUDA_OP_DIV; template <typename T> T operator()(T a, T b) const noexcept { return a / b; } };
+struct op_pow { static constexpr int device_op = -1; template <typename T> T operator()(T a, T b) const noexcept { return std::pow(a, b); } };
 
 template <typename Op>
 dsc_tensor *binary(dsc_ctx *ctx, const char *name, dsc_tensor *xa, dsc_tensor *xb, dsc_tensor *out, Op op) noexcept {
@@ -457,8 +458,8 @@ dsc_tensor *binary(dsc_ctx *ctx, const char *name, dsc_tensor *xa, dsc_tensor *x
         DSC_ASSERT(memcmp(out->shape, shape, sizeof(shape)) == 0);
     }
 
-    if constexpr (std::is_same_v<Op, op_mul>) {
-        if (dsc_try_device_cmul(ctx, xa, xb, out)) return out;      // device-resident spectra stay on the device
+    if constexpr (Op::device_op >= 0) {
+        if (dsc_try_device_binary(ctx, Op::device_op, xa, xb, out)) return out;   // device-resident data stays there
     }
 
     // operands are promoted through the scratch arena so nothing needs freeing afterwards
@@ -514,10 +515,11 @@ dsc_tensor *like_or_check(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, co
 
 // same dtype in and out
 template <typename Op>
-dsc_tensor *unary(dsc_ctx *ctx, const char *name, const dsc_tensor *x, dsc_tensor *out, Op op) noexcept {
+dsc_tensor *unary(dsc_ctx *ctx, const char *name, const dsc_tensor *x, dsc_tensor *out, Op op, const int device_op = -1) noexcept {
     DSC_ASSERT(x != nullptr);
     dsc_span span(name, "op;unary", nullptr);
     out = like_or_check(ctx, x, out, x->dtype);
+    if (device_op >= 0 && dsc_try_device_unary(ctx, device_op, x, out)) return out;
     dsc_host_needed(ctx, x);
     by_dtype(x->dtype, [&](auto *t) {
         using T = std::remove_pointer_t<decltype(t)>;
@@ -531,10 +533,11 @@ dsc_tensor *unary(dsc_ctx *ctx, const char *name, const dsc_tensor *x, dsc_tenso
 
 // complex (or real) in, real out
 template <typename Op>
-dsc_tensor *unary_to_real(dsc_ctx *ctx, const char *name, const dsc_tensor *x, dsc_tensor *out, Op op) noexcept {
+dsc_tensor *unary_to_real(dsc_ctx *ctx, const char *name, const dsc_tensor *x, dsc_tensor *out, Op op, const int device_op = -1) noexcept {
     DSC_ASSERT(x != nullptr);
     dsc_span span(name, "op;unary", nullptr);
     out = like_or_check(ctx, x, out, real_dtype(x->dtype));
+    if (device_op >= 0 && dsc_try_device_unary(ctx, device_op, x, out)) return out;
     dsc_host_needed(ctx, x);
     by_dtype(x->dtype, [&](auto *t) {
         using T = std::remove_pointer_t<decltype(t)>;
@@ -599,21 +602,21 @@ DSC_DEFINE_UNARY(dsc_sqrt, std::sqrt(v))
 #undef DSC_DEFINE_UNARY
 
 dsc_tensor *dsc_abs(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, dsc_tensor *DSC_RESTRICT out) noexcept {
-    return unary_to_real(ctx, "dsc_abs", x, out, [](auto v) noexcept { return std::abs(v); });
+    return unary_to_real(ctx, "dsc_abs", x, out, [](auto v) noexcept { return std::abs(v); }, DSC_CUDA_OP_ABS);
 }
 
 dsc_tensor *dsc_angle(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x) noexcept {
-    return unary_to_real(ctx, "dsc_angle", x, nullptr, [](auto v) noexcept { return std::arg(v); });
+    return unary_to_real(ctx, "dsc_angle", x, nullptr, [](auto v) noexcept { return std::arg(v); }, DSC_CUDA_OP_ANGLE);
 }
 
 dsc_tensor *dsc_imag(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x) noexcept {
-    return unary_to_real(ctx, "dsc_imag", x, nullptr, [](auto v) noexcept { return std::imag(v); });
+    return unary_to_real(ctx, "dsc_imag", x, nullptr, [](auto v) noexcept { return std::imag(v); }, DSC_CUDA_OP_IMAG);
 }
 
 dsc_tensor *dsc_real(dsc_ctx *ctx, dsc_tensor *DSC_RESTRICT x) noexcept {
     DSC_ASSERT(x != nullptr);
     if (x->dtype == F32 || x->dtype == F64) return x;       // identity, same pointer
-    return unary_to_real(ctx, "dsc_real", x, nullptr, [](auto v) noexcept { return std::real(v); });
+    return unary_to_real(ctx, "dsc_real", x, nullptr, [](auto v) noexcept { return std::real(v); }, DSC_CUDA_OP_REAL);
 }
 
 dsc_tensor *dsc_conj(dsc_ctx *ctx, dsc_tensor *DSC_RESTRICT x) noexcept {
@@ -622,7 +625,7 @@ dsc_tensor *dsc_conj(dsc_ctx *ctx, dsc_tensor *DSC_RESTRICT x) noexcept {
     return unary(ctx, "dsc_conj", x, nullptr, [](auto v) noexcept {
         if constexpr (is_cplx<decltype(v)>::value) return std::conj(v);
         else return v;
-    });
+    }, DSC_CUDA_OP_CONJ);
 }
 
 dsc_tensor *dsc_i0(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x) noexcept {

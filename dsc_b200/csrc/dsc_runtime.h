@@ -123,9 +123,11 @@ void dsc_dev_drop(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept;               
 void dsc_host_written(dsc_tensor_buffer *buf) noexcept;                            // host op wrote the payload
 void dsc_host_needed(dsc_ctx *ctx, const dsc_tensor *x) noexcept;                  // host op is about to read the payload
 
-// Complex product on the device when an operand already lives there (residency >= 1): same shape or xb a
-// row broadcast over xa.  Returns false when the host loop should run instead.
-bool dsc_try_device_cmul(dsc_ctx *ctx, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept;
+// Elementwise arithmetic / spectrum post-processing on the device when an operand already lives there
+// (residency >= 1).  binary: op = DSC_CUDA_OP_ADD..DIV, same dtype, xb same shape / one row / one element;
+// unary: op = DSC_CUDA_OP_ABS..CONJ on complex input.  Return false when the host loop should run instead.
+bool dsc_try_device_binary(dsc_ctx *ctx, int op, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept;
+bool dsc_try_device_unary(dsc_ctx *ctx, int op, const dsc_tensor *x, dsc_tensor *out) noexcept;
 
 // Crop along the last axis of a tensor whose current contents live only on the device (residency 2): download
 // just the kept columns [start, start + count) of every row into `out` (the README's y[:output_length] after

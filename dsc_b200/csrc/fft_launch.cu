@@ -10,6 +10,7 @@
 
 #include "dsc_cuda.h"
 #include "fft_dispatch.cuh"
+#include "pointwise_kernels.cuh"
 
 using namespace dscfft;
 
@@ -536,6 +537,40 @@ bool plan_ok(const dsc_cuda_plan *p) {
 
 // ---------------------------------------------------------------------------------------------
 
+namespace {
+inline int pointwise_blocks(long long total) {
+    const long long b = (total + 255) / 256;
+    return (int)(b < 148 * 32 ? b : 148 * 32);
+}
+template <typename T>
+int unary_by_op(int op, const void *x, void *out, long long n, void *stream) {
+    using V = cx<T>;
+    const int blocks = pointwise_blocks(n);
+    switch (op) {
+    case DSC_CUDA_OP_ABS: { auto k = pointwise_c2r<T, 0>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)x, (T *)out, n); break; }
+    case DSC_CUDA_OP_ANGLE: { auto k = pointwise_c2r<T, 1>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)x, (T *)out, n); break; }
+    case DSC_CUDA_OP_REAL: { auto k = pointwise_c2r<T, 2>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)x, (T *)out, n); break; }
+    case DSC_CUDA_OP_IMAG: { auto k = pointwise_c2r<T, 3>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)x, (T *)out, n); break; }
+    case DSC_CUDA_OP_CONJ: { auto k = pointwise_conj<T>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)x, (V *)out, n); break; }
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_unary: unknown op %d", op);
+    }
+    return check_launch("pointwise unary");
+}
+template <typename V>
+int binary_by_op(int op, const void *a, const void *b, void *out, long long rows, long long cols, int b_mode, void *stream) {
+    const int blocks = pointwise_blocks(rows * cols);
+    switch (op) {
+    case DSC_CUDA_OP_ADD: { auto k = pointwise_binary<V, 0>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)a, (const V *)b, (V *)out, rows, cols, b_mode); break; }
+    case DSC_CUDA_OP_SUB: { auto k = pointwise_binary<V, 1>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)a, (const V *)b, (V *)out, rows, cols, b_mode); break; }
+    case DSC_CUDA_OP_MUL: { auto k = pointwise_binary<V, 2>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)a, (const V *)b, (V *)out, rows, cols, b_mode); break; }
+    case DSC_CUDA_OP_DIV: { auto k = pointwise_binary<V, 3>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const V *)a, (const V *)b, (V *)out, rows, cols, b_mode); break; }
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary: unknown op %d", op);
+    }
+    return check_launch("pointwise binary");
+}
+}  // namespace
+
+
 extern "C" {
 
 const char *dsc_cuda_last_error(void) { return g_err; }
@@ -649,6 +684,27 @@ int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
                    (long long)rows, (long long)cols, b_rows);
     else return fail(DSC_CUDA_EINVAL, "dsc_cuda_cmul: dtype %d is not complex", dtype);
     return check_launch("cmul_rows");
+}
+
+int dsc_cuda_unary(int op, const void *x, int x_dtype, void *out, int64_t count, void *stream) {
+    if (!x || !out || count < 0) return fail(DSC_CUDA_EINVAL, "dsc_cuda_unary: bad argument");
+    if (count == 0) return 0;
+    if (x_dtype == DSC_CUDA_C32) return unary_by_op<float>(op, x, out, (long long)count, stream);
+    if (x_dtype == DSC_CUDA_C64) return unary_by_op<double>(op, x, out, (long long)count, stream);
+    return fail(DSC_CUDA_EINVAL, "dsc_cuda_unary: dtype %d is not complex", x_dtype);
+}
+
+int dsc_cuda_binary(int op, const void *a, const void *b, void *out, int dtype,
+                    int64_t rows, int64_t cols, int b_mode, void *stream) {
+    if (!a || !b || !out || rows < 0 || cols < 0 || b_mode < 0 || b_mode > 2) return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary: bad argument");
+    if (rows * cols == 0) return 0;
+    switch (dtype) {
+    case DSC_CUDA_F32: return binary_by_op<float>(op, a, b, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_F64: return binary_by_op<double>(op, a, b, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_C32: return binary_by_op<float2>(op, a, b, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_C64: return binary_by_op<double2>(op, a, b, out, rows, cols, b_mode, stream);
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary: unknown dtype %d", dtype);
+    }
 }
 
 int dsc_cuda_fill_twiddles(void *out, int64_t count, int64_t mult, int64_t denom, int dtype, void *stream) {

@@ -55,6 +55,9 @@ class CudaApi:
         L.dsc_cuda_irfft.argtypes = L.dsc_cuda_rfft.argtypes
         L.dsc_cuda_cmul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                     C.c_int, C.c_void_p]
+        L.dsc_cuda_unary.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        L.dsc_cuda_binary.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                      C.c_int, C.c_void_p]
         L.dsc_cuda_filter_work_bytes.restype = C.c_size_t
         L.dsc_cuda_filter_work_bytes.argtypes = [pp, C.c_int64]
         L.dsc_cuda_filter.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -96,6 +99,15 @@ class CudaApi:
     def cmul(self, a_ptr, b_ptr, out_ptr, dtype, rows, cols, b_rows, stream=0):
         self._check(self.lib.dsc_cuda_cmul(a_ptr, b_ptr, out_ptr, dtype, rows, cols, int(b_rows), stream),
                     "dsc_cuda_cmul")
+
+    def unary(self, op, x_ptr, x_dtype, out_ptr, count, stream=0):
+        """op: 0 abs, 1 angle, 2 real, 3 imag, 4 conj (DSC_CUDA_OP_*)."""
+        self._check(self.lib.dsc_cuda_unary(op, x_ptr, x_dtype, out_ptr, count, stream), "dsc_cuda_unary")
+
+    def binary(self, op, a_ptr, b_ptr, out_ptr, dtype, rows, cols, b_mode, stream=0):
+        """op: 0 add, 1 sub, 2 mul, 3 div; b_mode: 0 one row, 1 same shape, 2 one element."""
+        self._check(self.lib.dsc_cuda_binary(op, a_ptr, b_ptr, out_ptr, dtype, rows, cols, b_mode, stream),
+                    "dsc_cuda_binary")
 
     def fill_twiddles(self, out_ptr, count, mult, denom, dtype, stream=0):
         self._check(self.lib.dsc_cuda_fill_twiddles(out_ptr, count, mult, denom, dtype, stream), "dsc_cuda_fill_twiddles")

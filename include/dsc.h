@@ -274,6 +274,9 @@ extern dsc_tensor *dsc_fft_filter(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x
 extern void dsc_cuda_set_residency(dsc_ctx *ctx, int mode) noexcept;
 extern void dsc_cuda_sync_host(dsc_ctx *ctx, dsc_tensor *x) noexcept;
 extern void dsc_cuda_touch_host(dsc_ctx *ctx, dsc_tensor *x) noexcept;
+// residency >= 1: upload x's payload to its device mirror now (e.g. a filter spectrum or a window that
+// later device ops will read); no effect in strict mode
+extern void dsc_cuda_prefetch(dsc_ctx *ctx, dsc_tensor *x) noexcept;
 extern usize dsc_cuda_used_mem(dsc_ctx *ctx) noexcept;       // device-arena bytes in use
 extern usize dsc_cuda_alloc_calls(dsc_ctx *ctx) noexcept;    // device allocations made so far (stays 1)
 

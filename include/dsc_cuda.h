@@ -11,6 +11,8 @@
  *   dsc_cuda_fft         <- exec_fft + dsc_complex_fft  dsc/src/dsc.cpp:1958-2007, dsc_fft.h:156-176
  *   dsc_cuda_rfft/irfft  <- exec_rfft + dsc_real_fft    dsc/src/dsc.cpp:2102-2171, dsc_fft.h:178-238
  *   dsc_cuda_cmul        <- binary_op<mul_op> (complex) dsc/src/dsc.cpp:1186-1245, dsc_ops.h:68-78
+ *   dsc_cuda_unary       <- dsc_abs / dsc_angle / dsc_real / dsc_imag / dsc_conj  dsc.cpp:1480-1622
+ *   dsc_cuda_binary      <- dsc_add / dsc_sub / dsc_mul / dsc_div (same dtype)     dsc.cpp:1186-1310
  *   dsc_cuda_filter      <- README filterFFT            README.md:118-134 (rfft, *, irfft fused)
  *
  * Every entry point returns 0 on success or a negative DSC_CUDA_E* code; the message of
@@ -105,6 +107,18 @@ int dsc_cuda_filter(const dsc_cuda_plan *plan, const void *x, const void *spectr
  * or rows*cols (b_rows != 0). */
 int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
                   int64_t rows, int64_t cols, int b_rows, void *stream);
+
+/* Elementwise post-processing of device-resident data (one read + one write of the payload each).
+ * unary  : x complex (C32/C64) -> ABS, ANGLE, REAL, IMAG give the real dtype, CONJ the same complex dtype
+ *          (dsc_abs / dsc_angle / dsc_real / dsc_imag / dsc_conj, dsc/src/dsc.cpp:1480-1622).
+ * binary : out = a OP b for F32/F64/C32/C64 (both operands and out of `dtype`), rows x cols elements;
+ *          b_mode 0: b is one row of `cols` elements broadcast over the rows, 1: same shape, 2: b is one element
+ *          (dsc_add / dsc_sub / dsc_mul / dsc_div, dsc.cpp:1186-1310, dsc_ops.h:46-90).  out may alias a. */
+enum { DSC_CUDA_OP_ABS = 0, DSC_CUDA_OP_ANGLE = 1, DSC_CUDA_OP_REAL = 2, DSC_CUDA_OP_IMAG = 3, DSC_CUDA_OP_CONJ = 4 };
+enum { DSC_CUDA_OP_ADD = 0, DSC_CUDA_OP_SUB = 1, DSC_CUDA_OP_MUL = 2, DSC_CUDA_OP_DIV = 3 };
+int dsc_cuda_unary(int op, const void *x, int x_dtype, void *out, int64_t count, void *stream);
+int dsc_cuda_binary(int op, const void *a, const void *b, void *out, int dtype,
+                    int64_t rows, int64_t cols, int b_mode, void *stream);
 
 /* ---- building blocks of the multi-GPU four-step (one transform sharded over P GPUs) ----------
  * out[k] = exp(-2 pi i (k * mult mod denom) / denom), k < count: the two sqrt(M)-sized tables

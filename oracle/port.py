@@ -162,6 +162,41 @@ def cmul(a, b):
     return out.reshape(a.shape)
 
 
+def unary(name, x):
+    """Spectrum post-processing, numpy restatement of /root/reference/dsc/src/dsc.cpp:1480-1622:
+    abs = |z| (std::abs), angle = atan2(im, re) (std::arg), real / imag / conj exact; complex in, the
+    real dtype out (conj: same dtype)."""
+    x = np.ascontiguousarray(x)
+    real_dt = _REAL_OF[x.dtype]
+    if name == "abs":
+        return np.sqrt(x.real * x.real + x.imag * x.imag).astype(real_dt)
+    if name == "angle":
+        return np.arctan2(x.imag, x.real).astype(real_dt)
+    if name == "real":
+        return x.real.astype(real_dt)
+    if name == "imag":
+        return x.imag.astype(real_dt)
+    if name == "conj":
+        return np.conj(x)
+    raise ValueError(name)
+
+
+def binary(name, a, b):
+    """dsc_add / dsc_sub / dsc_mul / dsc_div for operands of one dtype with NumPy broadcasting
+    (/root/reference/dsc/src/dsc.cpp:1186-1310, functors dsc/include/dsc_ops.h:46-90)."""
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b, dtype=a.dtype)
+    if name == "add":
+        return (a + b).astype(a.dtype)
+    if name == "sub":
+        return (a - b).astype(a.dtype)
+    if name == "mul":
+        return (a * b).astype(a.dtype)
+    if name == "div":
+        return (a / b).astype(a.dtype)
+    raise ValueError(name)
+
+
 def filter_fft(s, b, fft_size):
     """README.md:118-134 filterFFT, uncropped: irfft(rfft(s, n) * rfft(b, n))."""
     S = rfft(s, n=fft_size)

@@ -99,8 +99,14 @@ class RefLib:
             f = getattr(lib, name)
             f.restype = _TP
             f.argtypes = [C.c_void_p, _TP, _TP, C.c_int, C.c_int]
-        lib.dsc_mul.restype = _TP
-        lib.dsc_mul.argtypes = [C.c_void_p, _TP, _TP, _TP]
+        for name in ("dsc_add", "dsc_sub", "dsc_mul", "dsc_div"):
+            getattr(lib, name).restype = _TP
+            getattr(lib, name).argtypes = [C.c_void_p, _TP, _TP, _TP]
+        lib.dsc_abs.restype = _TP
+        lib.dsc_abs.argtypes = [C.c_void_p, _TP, _TP]
+        for name in ("dsc_angle", "dsc_real", "dsc_imag", "dsc_conj"):
+            getattr(lib, name).restype = _TP
+            getattr(lib, name).argtypes = [C.c_void_p, _TP]
         lib.dsc_tensor_get_slice.restype = _TP
         lib.dsc_traces_record.argtypes = [C.c_void_p, C.c_bool]
         lib.dsc_dump_traces.argtypes = [C.c_void_p, C.c_char_p]
@@ -159,6 +165,24 @@ class RefLib:
         res = self.get(to)
         for t in (to, ta, tb):
             self.free(t)
+        return res
+
+    def binary(self, name, a, b):
+        """dsc_add / dsc_sub / dsc_mul / dsc_div with the reference's broadcasting (dsc.cpp:1186-1310)."""
+        ta, tb = self.put(a), self.put(b)
+        to = getattr(self.lib, f"dsc_{name}")(self.ctx, ta, tb, None)
+        res = self.get(to)
+        for t in (to, ta, tb):
+            self.free(t)
+        return res
+
+    def unary(self, name, x):
+        """dsc_abs / dsc_angle / dsc_real / dsc_imag / dsc_conj of a complex tensor (dsc.cpp:1480-1622)."""
+        tx = self.put(x)
+        to = self.lib.dsc_abs(self.ctx, tx, None) if name == "abs" else getattr(self.lib, f"dsc_{name}")(self.ctx, tx)
+        res = self.get(to)
+        self.free(to)
+        self.free(tx)
         return res
 
     def filter_fft(self, s, b, fft_size):

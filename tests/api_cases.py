@@ -165,6 +165,46 @@ def check_residency_modes(dsc):
         dsc.set_residency(0)
 
 
+def check_device_pointwise(dsc):
+    """|X|, arg X, Re, Im, conj and add/sub/mul/div against what the unmodified reference
+    returned for the same inputs -- through the host loops (strict mode) and through the device kernels
+    (operands made device-resident first; in mode 2 the results are downloaded lazily)."""
+    gold = [(m, a) for _, m, a in load_golden() if m["op"].startswith(("unary:", "binary:"))]
+    assert len(gold) >= 58
+    fn = {"abs": dsc.abs, "angle": dsc.angle, "real": dsc.real, "imag": dsc.imag, "conj": dsc.conj,
+          "add": dsc.add, "sub": dsc.sub, "mul": dsc.mul, "div": dsc.true_div}
+    exact = ("real", "imag", "conj", "add", "sub")
+    try:
+        for mode in (0, 1, 2):
+            dsc.set_residency(mode)
+            for meta, arrs in gold:
+                kind, name = meta["op"].split(":")
+                x = dsc.from_numpy(arrs["x"])
+                dsc.prefetch(x)
+                if kind == "unary":
+                    got = fn[name](x)
+                else:
+                    b = dsc.from_numpy(arrs["b"])
+                    got = fn[name](x, b)
+                want = arrs["y"]
+                g = got.numpy()
+                assert g.shape == want.shape and g.dtype == want.dtype, (meta, mode)
+                if name in exact:
+                    assert np.array_equal(g, want), (meta, mode)
+                else:
+                    assert rel_l2(g, want) < TOL[want.dtype] * 1e-1, (meta, mode, rel_l2(g, want))
+            # post-processing chained behind a transform: nothing goes back to the host in between
+            z = randn(np.random.default_rng(5), (4, 256), "complex64")
+            Z = dsc.fft(z)
+            mag, ph = dsc.abs(Z), dsc.angle(Z)
+            ref = port.fft(z)
+            assert rel_l2(mag.numpy(), np.abs(ref)) < 1e-5
+            assert rel_l2(mag.numpy() * np.exp(1j * ph.numpy()), ref) < 1e-5
+            del Z, mag, ph
+    finally:
+        dsc.set_residency(0)
+
+
 def check_traces(dsc):
     rng = np.random.default_rng(17)
     x = dsc.from_numpy(randn(rng, (4, 64), "float32"))

@@ -133,6 +133,26 @@ def main():
         sweep.append(ref.used_mem() - base)
     meta.append({"op": "plan_sweep", "n": 20, "axis": -1, "used_after_round": sweep})
 
+    # spectrum post-processing and arithmetic, appended last so that the earlier cases keep
+    # their indices and random streams: |X|, arg X, Re, Im, conj; add/sub/mul/div with same-shape, row and scalar b
+    for dt in CPLX:
+        z = randn(rng, (7, 33), dt)
+        for name in ("abs", "angle", "real", "imag", "conj"):
+            i = len(meta)
+            meta.append({"op": f"unary:{name}", "n": -1, "axis": -1})
+            blob[f"x{i}"] = z
+            blob[f"y{i}"] = ref.unary(name, z)
+    for dt in REAL + CPLX:
+        a = randn(rng, (6, 40), dt)
+        for bshape in ((6, 40), (40,), (1,)):
+            b = randn(rng, bshape, dt)
+            for name in ("add", "sub", "mul", "div"):
+                i = len(meta)
+                meta.append({"op": f"binary:{name}", "n": -1, "axis": -1})
+                blob[f"x{i}"] = a
+                blob[f"b{i}"] = b
+                blob[f"y{i}"] = ref.binary(name, a, b)
+
     blob["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(OUT, **blob)
     ref.close()

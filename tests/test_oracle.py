@@ -22,6 +22,16 @@ def test_port_matches_golden(i, meta, arrs):
         got = port.filter_fft(arrs["x"], arrs["b"], meta["n"])
     elif op == "mul":
         got = port.cmul(arrs["x"], arrs["b"])
+    elif op.startswith(("unary:", "binary:")):
+        kind, name = op.split(":")
+        got = port.unary(name, arrs["x"]) if kind == "unary" else port.binary(name, arrs["x"], arrs["b"])
+        want = arrs["y"]
+        assert got.shape == want.shape and got.dtype == want.dtype
+        if name in ("real", "imag", "conj", "add", "sub"):
+            assert np.array_equal(got, want)
+        else:   # libm / fused-multiply-add differences of one rounding
+            assert rel_l2(got, want) < TOL[want.dtype] / 50
+        return
     else:
         got = getattr(port, op)(arrs["x"], meta["n"], meta["axis"])
     want = arrs["y"]
