@@ -58,7 +58,7 @@ KernelEntry make_entry() {
     e.fn = fft_lines<T, LG_N, LG_E, LPB, FWD, MODE>;
     e.lpb = LPB;
     e.threads = LPB * Sc::TT;
-    e.smem = LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>), MODE == MODE_FAST ? Sc::TT : 0) * (int)sizeof(cx<T>);
+    e.smem = LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>), mode_is_dense(MODE) ? Sc::TT : 0) * (int)sizeof(cx<T>);
     e.configured = false;
     return e;
 }
@@ -85,6 +85,8 @@ DSC_DECLARE_TABLE(double, true, MODE_R2C, false)  DSC_DECLARE_TABLE(double, fals
 DSC_DECLARE_TABLE(float, true, MODE_FILTER, false) DSC_DECLARE_TABLE(double, true, MODE_FILTER, false)
 DSC_DECLARE_TABLE(float, true, MODE_FAST, false)  DSC_DECLARE_TABLE(float, false, MODE_FAST, false)
 DSC_DECLARE_TABLE(double, true, MODE_FAST, false) DSC_DECLARE_TABLE(double, false, MODE_FAST, false)
+DSC_DECLARE_TABLE(float, true, MODE_R2C_FAST, false)  DSC_DECLARE_TABLE(float, false, MODE_C2R_FAST, false)
+DSC_DECLARE_TABLE(double, true, MODE_R2C_FAST, false) DSC_DECLARE_TABLE(double, false, MODE_C2R_FAST, false)
 #undef DSC_DECLARE_TABLE
 
 // ---- fused four-step launches ------------------------------------------------------------------

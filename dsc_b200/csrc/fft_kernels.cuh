@@ -37,8 +37,11 @@ enum Mode : int {
     MODE_C2R = 2,   // irfft: N+1 bins -> 2N reals, mixing fused before the first stage
     MODE_FAST = 3,  // dense complex lines (inner == 1, no pad/crop, whole blocks): the bandwidth path --
                     // one base pointer per thread, immediate offsets, streaming cache hints
+    MODE_R2C_FAST = 4,  // MODE_R2C / MODE_C2R for dense last-axis lines in whole blocks, full-length input: compile-
+    MODE_C2R_FAST = 5,  // time geometry, vector accesses, no shared-memory pass outside the butterfly exchanges
     MODE_FILTER = 6,  // rfft -> times a spectrum -> irfft in ONE kernel: the spectrum never leaves shared memory
 };
+__host__ __device__ constexpr bool mode_is_dense(int mode) { return mode == MODE_FAST || mode == MODE_R2C_FAST || mode == MODE_C2R_FAST; }
 
 // how MODE_C2C reads its input
 enum InKind : int {
@@ -80,6 +83,8 @@ struct FftArgs {
     long long ring_out;
     double scale;         // applied to the outputs when do_scale (1/N of the inverse)
     int do_scale;
+    int packed_in;        // real pairs are adjacent and vector-aligned in every line: load them as one complex
+    int packed_out;       // same for the real output of MODE_C2R / MODE_FILTER
     int keep_out;         // four-step second pass: 1 = a later kernel re-reads the output soon (plain stores, the
                           // rows stay in L2); 0 = streaming stores
 };
@@ -295,7 +300,7 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     const int tid = threadIdx.x;
     int l, t;
     if (a.strided) { l = tid % LPB; t = tid / LPB; } else { l = tid / TT; t = tid % TT; }
-    constexpr int LINE = Sc::line_stride(LPB, (int)sizeof(V), MODE == MODE_FAST ? TT : 0);
+    constexpr int LINE = Sc::line_stride(LPB, (int)sizeof(V), mode_is_dense(MODE) ? TT : 0);
     V *sm = sm_all + l * LINE;
     // A line's exchanges need: a warp barrier when the line lives inside one warp; its own hardware
     // barrier when it is a whole number of warps and the block has few enough lines (lines then
@@ -348,6 +353,35 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
             for (int c = 0; c < E; ++c) v[c] = sm[Sc::pad_read(t, pt, c)];
             __syncthreads();
         }
+    } else if constexpr (MODE == MODE_R2C_FAST) {
+        // 2N dense reals = N complex, one vector load per point
+        const V *__restrict__ xp = (const V *)a.x + line * N + t;
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = ld_stream(xp + c * TT);
+    } else if constexpr (MODE == MODE_C2R_FAST) {
+        // Every thread builds the packed points z[t + c TT] it needs for the first butterfly itself, from the bin
+        // pair (k, N-k) of each: two loads per point (every bin is wanted by two threads of the block; the second
+        // request hits L1) instead of a pass through shared memory with two block barriers before the transform
+        // can start.  z[k] is the first result of the pair step when k < N/2 and the second one of pair N-k
+        // otherwise (dsc_fft.h:199-214, c = +1/2).
+        // (instantiated for every length of the table; the launcher only uses it from real_fast_min_lg() up)
+        const V *__restrict__ xc = (const V *)a.x + line * (N + 1);
+        const V *__restrict__ twr = (const V *)a.tw_real;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            constexpr int HALF = E / 2;
+            const bool upper = c >= HALF;
+            const int k = t + c * TT;
+            const int kk = upper ? N - k : k;
+            const V lo = __ldg(xc + kk), hi = __ldg(xc + (N - kk));
+            V ra, rb;
+            real_pair<false, T>(lo, hi, __ldg(twr + kk), ra, rb);
+            v[c] = upper ? rb : ra;
+            if (t == 0) {
+                if (c == 0) v[c] = mk<T>((T)0.5 * (lo.x + hi.x), (T)0.5 * (lo.x - hi.x));   // DC + Nyquist, real parts only
+                if (c == HALF) v[c] = mk<T>(lo.x, -lo.y);                                   // bin N/2
+            }
+        }
     } else if constexpr (MODE == MODE_C2R) {
         // bins X[0..N] -> packed z[0..N); DC/Nyquist use real parts only (dsc_fft.h:227-228)
         const V *__restrict__ xc = (const V *)a.x + ibase;
@@ -378,12 +412,23 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     } else if (MODE == MODE_R2C || MODE == MODE_FILTER || a.in_kind == IN_PAIRS) {
         // 2N reals seen as N complex: z[j] = (x[..2j], x[..2j+1]); gi is in REAL elements
         const T *__restrict__ xr = (const T *)a.x + ibase;
+        if (a.packed_in) {
+            // adjacent reals in aligned rows (last axis): one vector load per pair instead of two scalar loads
+            // that each use half of every sector
 #pragma unroll
-        for (int c = 0; c < E; ++c) {
-            const long long off = ioff0 + c * istep;
-            const T re = off < lim ? ld_pol<POL_IN>(xr + off) : (T)0;
-            const T im = off + a.gi_pstride < lim ? ld_pol<POL_IN>(xr + off + a.gi_pstride) : (T)0;
-            v[c] = mk<T>(re, im);
+            for (int c = 0; c < E; ++c) {
+                const long long off = ioff0 + c * istep;
+                if (off + 1 < lim) v[c] = __ldcs((const V *)(xr + off));
+                else v[c] = mk<T>(off < lim ? xr[off] : (T)0, (T)0);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const long long off = ioff0 + c * istep;
+                const T re = off < lim ? ld_pol<POL_IN>(xr + off) : (T)0;
+                const T im = off + a.gi_pstride < lim ? ld_pol<POL_IN>(xr + off + a.gi_pstride) : (T)0;
+                v[c] = mk<T>(re, im);
+            }
         }
     } else if (a.in_kind == IN_REAL) {
         const T *__restrict__ xr = (const T *)a.x + ibase;
@@ -479,6 +524,34 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
             V *__restrict__ ob = (V *)a.out + block * (long long)(LPB * N);
             for (int e = tid; e < LPB * N; e += THREADS) st_stream(ob + e, sm_all[(e / N) * LINE + Sc::pad(e % N)]);
         }
+    } else if constexpr (MODE == MODE_C2R_FAST) {
+        V *__restrict__ op = (V *)a.out + line * N + t;
+#pragma unroll
+        for (int c = 0; c < E; ++c) st_stream(op + c * TT, v[c]);
+    } else if constexpr (MODE == MODE_R2C_FAST) {
+        // Z[k] is in registers; the partner Z[N-k] of each of the thread's first E/2 points comes from shared
+        // memory (every thread only overwrites the slots it read last, so no barrier is needed before the writes)
+        const int pt = Sc::pad(t);
+#pragma unroll
+        for (int c = 0; c < E; ++c) sm[Sc::pad_read(t, pt, c)] = v[c];
+        line_sync(ls);
+        V *__restrict__ oc = (V *)a.out + line * (N + 1);
+        const V *__restrict__ twr = (const V *)a.tw_real;
+#pragma unroll
+        for (int c = 0; c < E / 2; ++c) {
+            const int k = t + c * TT;
+            if (c == 0 && t == 0) {
+                const V z0 = v[0], zh = v[E / 2];          // thread 0 also owns point N/2
+                st_stream(oc, mk<T>(z0.x + z0.y, (T)0));
+                st_stream(oc + N, mk<T>(z0.x - z0.y, (T)0));
+                st_stream(oc + N / 2, mk<T>(zh.x, -zh.y));
+            } else {
+                V xa, xb;
+                real_pair<true, T>(v[c], sm[Sc::pad(N - k)], __ldg(twr + k), xa, xb);
+                st_stream(oc + k, xa);
+                st_stream(oc + (N - k), xb);
+            }
+        }
     } else if constexpr (IS_C2C) {
         if (a.four_shift) {   // four-step first pass: times W_M^(in * k1)
             const unsigned q = (unsigned)in;
@@ -495,10 +568,15 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
         // N complex = 2N reals; go is in REAL elements
         if (active) {
             T *__restrict__ orl = (T *)a.out + obase + ooff0;
+            if (a.packed_out) {
 #pragma unroll
-            for (int c = 0; c < E; ++c) {
-                orl[c * ostep] = v[c].x;
-                orl[c * ostep + a.go_pstride] = v[c].y;
+                for (int c = 0; c < E; ++c) __stcs((V *)(orl + c * ostep), v[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    orl[c * ostep] = v[c].x;
+                    orl[c * ostep + a.go_pstride] = v[c].y;
+                }
             }
         }
     } else {  // MODE_R2C: Z -> shared memory, then each thread un-mixes its bin pairs

@@ -152,7 +152,7 @@ int build_tables(dsc_cuda_plan *p, const PlanLayout &L, void *stream) {
 
 inline int pow2_shift(long long v);
 
-int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a_in, void *stream) {
+int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a_in, void *stream, size_t real_bytes = 0) {
     KernelEntry &e = table[lg_n];
 #if !defined(DSC_EMUL)
     if (!e.configured) {
@@ -167,6 +167,14 @@ int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a_in, void *stream
     if (a_in.lines <= 0) return 0;
     FftArgs a = a_in;
     a.inner_shift = pow2_shift(a.inner);
+    // packed real pairs (last-axis rfft / irfft / filter): vector accesses when every line starts aligned
+    {
+        const size_t vec = 2 * real_bytes;
+        a.packed_in = real_bytes && a.gi_pstride == 1 && a.gi.estride == 2 && a.inner == 1 && a.gi.ostride % 2 == 0 &&
+                      (uintptr_t)a.x % vec == 0;
+        a.packed_out = real_bytes && a.go_pstride == 1 && a.go.estride == 2 && a.inner == 1 && a.go.ostride % 2 == 0 &&
+                       (uintptr_t)a.out % vec == 0;
+    }
     if (a.lines % e.lpb != 0) a.no_limit = 0;
     const long long blocks = (a.lines + e.lpb - 1) / e.lpb;
     if (blocks > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "too many lines for one grid: %lld", a.lines);
@@ -204,6 +212,9 @@ inline long long l2_chunk_rows(size_t row_bytes) {
     const long long r = (long long)(budget / (row_bytes ? row_bytes : 1));
     return r > 1 ? r : 1;
 }
+
+// shortest complex order (log2) served by the dense packed-real kernels: a line must span at least a warp
+template <typename T> constexpr int real_fast_min_lg() { return Tile<T>::LG_E + 5; }
 
 inline size_t in_elem_size(const FftArgs &a, size_t real_size) {
     return (a.in_kind == IN_REAL || a.in_kind == IN_PAIRS) ? real_size : 2 * real_size;
@@ -387,7 +398,12 @@ int run_rfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, 
         set_stage_tables<T>(a, p->tw1);
         a.tw_real = p->tw_real;
         a.strided = inner > 1;
-        return launch_lines(get_table<T, true, MODE_R2C, false>(), p->lg_n, a, stream);
+        // dense last-axis lines in whole blocks, no pad / crop: the bandwidth path
+        KernelEntry *fast = get_table<T, true, MODE_R2C_FAST, false>();
+        if (inner == 1 && x_n == 2 * n && p->lg_n >= real_fast_min_lg<T>() && a.lines % fast[p->lg_n].lpb == 0 &&
+            (uintptr_t)x % (2 * sizeof(T)) == 0)
+            return launch_lines(fast, p->lg_n, a, stream);
+        return launch_lines(get_table<T, true, MODE_R2C, false>(), p->lg_n, a, stream, sizeof(T));
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass rfft (order %lld) along a strided axis", n);
     // packed complex transform into the bin rows (stride n+1), then un-mix the bin pairs in place
@@ -437,7 +453,11 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
         a.tw_real = p->tw_real;
         a.strided = inner > 1;
         a.do_scale = 1; a.scale = 1.0 / (double)n;               // 2/(2n), dsc_fft.h:232
-        return launch_lines(get_table<T, false, MODE_C2R, false>(), p->lg_n, a, stream);
+        KernelEntry *fast = get_table<T, false, MODE_C2R_FAST, false>();
+        if (inner == 1 && x_n == n + 1 && p->lg_n >= real_fast_min_lg<T>() && a.lines % fast[p->lg_n].lpb == 0 &&
+            (uintptr_t)out % (2 * sizeof(T)) == 0)
+            return launch_lines(fast, p->lg_n, a, stream);
+        return launch_lines(get_table<T, false, MODE_C2R, false>(), p->lg_n, a, stream, sizeof(T));
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass irfft (order %lld) along a strided axis", n);
     // work = [ packed z rows of the chunk | four-step work ]
@@ -490,7 +510,7 @@ int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void
         a.tw_real = p->tw_real;
         a.filt = spectrum;
         a.do_scale = 1; a.scale = 1.0 / (double)n;
-        return launch_lines(get_table<T, true, MODE_FILTER, false>(), p->lg_n, a, stream);
+        return launch_lines(get_table<T, true, MODE_FILTER, false>(), p->lg_n, a, stream, sizeof(T));
     }
     // rows in flight: packed spectrum rows of the chunk + four-step work
     const size_t row_bytes = (size_t)n * sizeof(V);

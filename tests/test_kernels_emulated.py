@@ -101,6 +101,26 @@ def test_rfft_irfft_last_axis(dev, dtype, lg):
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("lg", [8, 9, 10, 11, 12])
+def test_rfft_irfft_dense_whole_blocks(dev, dtype, lg):
+    """16 full-length last-axis lines: whole blocks for every block shape, so the dense packed-real kernels run
+    (vector accesses, every thread builds its own packed points from the bin pairs); DC / Nyquist imaginary
+    parts of the irfft input are ignored (dsc_fft.h:227-228)."""
+    rng = np.random.default_rng(300 + lg)
+    x = randn(rng, (16, 2 << lg), dtype)
+    y = dev.rfft(x)
+    want = port.rfft(x)
+    assert rel_l2(y, want) < TIGHT[dtype]
+    assert np.all(y[:, 0].imag == 0) and np.all(y[:, -1].imag == 0)
+    bins = want.copy()
+    bins[:, 0] += 3j
+    bins[:, -1] -= 2j
+    z = dev.irfft(bins)
+    assert rel_l2(z, port.irfft(want)) < TIGHT[dtype]
+    assert rel_l2(z, x) < TIGHT[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
 def test_rfft_axes_and_length_rules(dev, dtype):
     rng = np.random.default_rng(9)
     cdt = np.complex64 if dtype == "float32" else np.complex128
