@@ -193,6 +193,10 @@ def test_two_pass_real(dev, dtype, lg):
     assert rel_l2(dev.rfft(xs, n=2 << lg), port.rfft(xs, n=2 << lg)) < TIGHT[dtype]
     Xs = want[:, :-5]                                  # fewer bins than order+1
     assert rel_l2(dev.irfft(Xs, n=want.shape[1]), port.irfft(Xs, n=want.shape[1])) < TIGHT[dtype]
+    bins = want.copy()                                 # imaginary parts of DC / Nyquist are ignored (dsc_fft.h:227-228)
+    bins[:, 0] += 3j
+    bins[:, -1] -= 2j
+    assert rel_l2(dev.irfft(bins), port.irfft(want)) < TIGHT[dtype]
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
