@@ -945,12 +945,14 @@ __global__ void real_mix_rows(const cx<T> *__restrict__ x, cx<T> *__restrict__ z
                               int shift, int mask) {
     using V = cx<T>;
     const int half = n / 2;                 // work items per row: k = 0 .. half-1 (k = 0 also does n/2, n)
+    int lg_half = 0;
+    while ((1 << lg_half) < half) ++lg_half;
     const long long total = rows * (long long)half;
     const V zero = mk<T>((T)0, (T)0);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long row = i / half;
-        const int k = (int)(i % half);
+        const long long row = i >> lg_half;             // n is a power of two: no 64-bit division per item
+        const int k = (int)(i & (half - 1));
         if (FWD) {
             V *zr = z + row * (long long)(n + 1);
             if (k == 0) {
@@ -994,11 +996,13 @@ __global__ void filter_pairs_rows(cx<T> *__restrict__ z, const cx<T> *__restrict
                                   const cx<T> *__restrict__ tw_lo, const cx<T> *__restrict__ tw_hi, int shift, int mask) {
     using V = cx<T>;
     const int half = n / 2;
+    int lg_half = 0;
+    while ((1 << lg_half) < half) ++lg_half;
     const long long total = rows * (long long)half;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long row = i / half;
-        const int k = (int)(i - row * half);
+        const long long row = i >> lg_half;
+        const int k = (int)(i & (half - 1));
         V *zr = z + row * (long long)n;
         if (k == 0) {
             zr[0] = filter_dc<T>(zr[0], __ldg(spectrum), __ldg(spectrum + n));
