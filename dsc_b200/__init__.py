@@ -103,6 +103,7 @@ def _load():
     L.dsc_cuda_sync_host.argtypes = [C.c_void_p, _TP]
     L.dsc_cuda_touch_host.argtypes = [C.c_void_p, _TP]
     L.dsc_cuda_prefetch.argtypes = [C.c_void_p, _TP]
+    L.dsc_cuda_download_async.argtypes = [C.c_void_p, _TP]
     _lib = L
     return L
 
@@ -332,6 +333,11 @@ def set_residency(mode: int) -> None:
 def prefetch(x: Tensor) -> None:
     """Upload x to its device mirror now (residency >= 1), so that later ops on it run on the device."""
     _load().dsc_cuda_prefetch(_get_ctx(), x.c)
+
+
+def download_async(x: Tensor) -> None:
+    """Residency 2: start the device -> host copy of x and return; sync_host(x) / x.numpy() waits for it."""
+    _load().dsc_cuda_download_async(_get_ctx(), x.c)
 
 
 def sync_host(x: Tensor) -> None:

@@ -195,6 +195,13 @@ static void dev_unlink(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
 
 static void download_now(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     byte *host = (byte *) buf + BUFFER_HEADER;
+    if (buf->flags & DSC_BUF_DOWNLOADING) {            // started by dsc_cuda_download_async: just wait for it
+        dscdev::event_wait(buf->downloaded);           // (this copy only: later downloads may still be in flight)
+        dscdev::event_release(buf->downloaded);
+        buf->downloaded = nullptr;
+        buf->flags &= ~(DSC_BUF_HOST_STALE | DSC_BUF_DOWNLOADING);
+        return;
+    }
     dscdev::stream_sync(0);
     dscdev::copy_d2h(host, ctx->dev_base + ctx->dev_alloc.nodes[buf->dev_node].off, buf->nbytes, 2);
     dscdev::stream_sync(2);
@@ -344,6 +351,21 @@ void dsc_cuda_sync_host(dsc_ctx *ctx, dsc_tensor *x) noexcept { dsc_host_needed(
 
 void dsc_cuda_touch_host(dsc_ctx *, dsc_tensor *x) noexcept { if (x) dsc_host_written(x->buffer); }
 
+void dsc_cuda_download_async(dsc_ctx *ctx, dsc_tensor *x) noexcept {
+    // residency 2: start the device -> host copy of a result on the download stream and return; the next calls
+    // (uploads and kernels of the following transform) overlap with it -- PCIe is full duplex -- and
+    // dsc_cuda_sync_host / any host access of x waits for it.
+    if (x == nullptr || !ctx->has_device) return;
+    dsc_tensor_buffer *b = x->buffer;
+    if (!(b->flags & DSC_BUF_HOST_STALE) || (b->flags & DSC_BUF_DOWNLOADING) || b->dev_node < 0) return;
+    dscdev::Event *produced = dscdev::event_record(0);
+    dscdev::stream_wait(2, produced);
+    dscdev::event_release(produced);
+    dscdev::copy_d2h((byte *) b + BUFFER_HEADER, ctx->dev_base + ctx->dev_alloc.nodes[b->dev_node].off, b->nbytes, 2);
+    b->downloaded = dscdev::event_record(2);
+    b->flags |= DSC_BUF_DOWNLOADING;
+}
+
 void dsc_cuda_prefetch(dsc_ctx *ctx, dsc_tensor *x) noexcept {
     if (x == nullptr || !ctx->has_device || ctx->residency < 1 || x->buffer->nbytes == 0) return;
     operand_on_device(ctx, x);
@@ -372,6 +394,7 @@ DSC_MALLOC dsc_tensor *dsc_new_tensor(dsc_ctx *ctx, const int n_dim, const int *
         buffer->busy = 0;
         buffer->nbytes = nbytes;
         buffer->dev_prev = buffer->dev_next = nullptr;
+        buffer->downloaded = nullptr;
     }
     buffer->refs++;
 

@@ -39,6 +39,7 @@ void copy_d2h_2d(void *dst_host, size_t dst_pitch, const void *src_dev, size_t s
 Event *event_record(int which_stream);          // from a small recycled pool
 void stream_wait(int which_stream, Event *e);
 float event_ms(Event *start, Event *stop);      // both must have completed
+void event_wait(Event *e);                      // block the host until the event has completed
 void event_release(Event *e);
 
 }  // namespace dscdev

@@ -107,6 +107,7 @@ float event_ms(Event *a, Event *b) {
     CUDA_OK(cudaEventElapsedTime(&ms, a->ev, b->ev));
     return ms;
 }
+void event_wait(Event *e) { CUDA_OK(cudaEventSynchronize(e->ev)); }
 void event_release(Event *e) { if (e) g_free_events.push_back(e); }
 
 }  // namespace dscdev

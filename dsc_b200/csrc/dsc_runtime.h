@@ -68,6 +68,7 @@ enum : int {
     DSC_BUF_DEV_VALID  = 1,   // device mirror holds the current contents
     DSC_BUF_HOST_STALE = 2,   // residency mode 2: host copy not yet downloaded
     DSC_BUF_SCRATCH    = 4,   // lives in the scratch arena (never freed individually)
+    DSC_BUF_DOWNLOADING = 8,  // dsc_cuda_download_async: the device -> host copy is in flight on the download stream
 };
 
 struct dsc_tensor_buffer {
@@ -77,6 +78,7 @@ struct dsc_tensor_buffer {
     int busy;                       // operand of the running op: its mirror must not be evicted
     usize nbytes;                   // payload bytes
     dsc_tensor_buffer *dev_prev, *dev_next;   // list of buffers that own a device mirror
+    dscdev::Event *downloaded;      // DSC_BUF_DOWNLOADING: completes when the asynchronous download has landed
 };
 
 struct dsc_fft_plan {

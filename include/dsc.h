@@ -274,6 +274,9 @@ extern dsc_tensor *dsc_fft_filter(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x
 extern void dsc_cuda_set_residency(dsc_ctx *ctx, int mode) noexcept;
 extern void dsc_cuda_sync_host(dsc_ctx *ctx, dsc_tensor *x) noexcept;
 extern void dsc_cuda_touch_host(dsc_ctx *ctx, dsc_tensor *x) noexcept;
+// residency 2: start downloading x's payload and return; later calls overlap with the copy (uploads of the next
+// transform run in the other PCIe direction); dsc_cuda_sync_host(x) or any host access of x waits for it
+extern void dsc_cuda_download_async(dsc_ctx *ctx, dsc_tensor *x) noexcept;
 // residency >= 1: upload x's payload to its device mirror now (e.g. a filter spectrum or a window that
 // later device ops will read); no effect in strict mode
 extern void dsc_cuda_prefetch(dsc_ctx *ctx, dsc_tensor *x) noexcept;

@@ -161,6 +161,16 @@ def check_residency_modes(dsc):
                 assert rel_l2(crop[r], port.filter_fft(sig[r], taps, 2048)[:1036]) < 1e-5
             assert rel_l2(yf[:, 100:300].numpy(), yf.numpy()[:, 100:300]) == 0.0
             del S, B, yf
+            # double-buffered results: the download of one result overlaps the next transform (no-op in mode 1)
+            xs = [randn(rng, (16, 1024), "complex64") for _ in range(3)]
+            pending = []
+            for xi in xs:
+                zi = dsc.ifft(dsc.fft(xi))
+                dsc.download_async(zi)
+                pending.append(zi)
+            for xi, zi in zip(xs, pending):
+                assert rel_l2(zi.numpy(), xi) < 1e-6
+            del pending
     finally:
         dsc.set_residency(0)
 

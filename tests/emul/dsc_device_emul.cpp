@@ -36,5 +36,6 @@ void copy_d2h_2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t 
 Event *event_record(int) { return new Event{now_ms()}; }
 void stream_wait(int, Event *) {}
 float event_ms(Event *a, Event *b) { return (float)(b->t - a->t); }
+void event_wait(Event *) {}
 void event_release(Event *e) { delete e; }
 }  // namespace dscdev

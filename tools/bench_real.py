@@ -48,3 +48,23 @@ for lg in (8, 10, 11, 12, 13, 14, 15, 16, 18, 20):
     run(lg)
 for lg in (10, 12, 13, 14, 16, 18):
     run(lg, 1)
+
+
+def run_filter(lg_real, total_bytes=1 << 30):
+    nreal = 1 << lg_real
+    order = nreal // 2
+    rows = total_bytes // (nreal * 4)
+    x = torch.randn(rows, nreal, dtype=torch.float32, device=dev)
+    B = torch.randn(order + 1, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    nb = api.plan_bytes(order, cuda_api.FFT_REAL, 0)
+    pm = torch.empty(nb, dtype=torch.uint8, device=dev)
+    plan = api.plan_build(order, cuda_api.FFT_REAL, 0, pm.data_ptr(), nb)
+    wb = api.filter_work_bytes(plan, rows)
+    work = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
+    t = timed(lambda: api.filter(plan, x.data_ptr(), B.data_ptr(), y.data_ptr(), rows, nreal, work.data_ptr(), wb))
+    print(f"filter 2^{lg_real} float32 rows={rows}: {t:.3f} ms {2 * x.numel() * 4 / t / 1e6:.0f} GB/s", flush=True)
+
+
+for lg in (10, 12, 13, 14, 15):
+    run_filter(lg)
