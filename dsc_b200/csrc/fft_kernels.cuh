@@ -611,8 +611,17 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
     }
 }
 
+// Resident blocks per SM the register allocation must allow.  The float 4096-point bandwidth kernel compiles to
+// 56 registers = 4 blocks of 256 threads; capping it at 51 (5 blocks, 40 warps/SM) costs no spills and was
+// measured +1.2-1.7 % in same-box A/B runs (0.881 -> 0.892-0.896 of the copy peak); 6 blocks (42 registers)
+// spill and lose 15 %.  Shorter float
+// lines and all double lines spill a few registers under the same cap and gain nothing, so they keep 4 blocks.
+template <typename T> __host__ __device__ constexpr int lines_min_blocks(int mode, int lg_n) {
+    return (mode == MODE_FAST && sizeof(T) == 4 && lg_n == 12) ? 5 : 1;
+}
+
 template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
-__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)))
+__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)), lines_min_blocks<T>(MODE, LG_N))
 fft_lines(const FftArgs a) {
     DSC_DYN_SMEM(smem_raw);
     fft_lines_body<T, LG_N, LG_E, LPB, FWD, MODE>(a, (long long)blockIdx.x, smem_raw);
