@@ -85,6 +85,8 @@ struct FftArgs {
     int do_scale;
     int packed_in;        // real pairs are adjacent and vector-aligned in every line: load them as one complex
     int packed_out;       // same for the real output of MODE_C2R / MODE_FILTER
+    int seg_shift;        // four-step first pass, dense rows: a row is made of segments of 2^seg_shift elements that lie
+    long long seg_extra;  // seg_extra elements further apart than their length (0 / 0: one contiguous row)
     int keep_out;         // four-step second pass: 1 = a later kernel re-reads the output soon (plain stores, the
                           // rows stay in L2); 0 = streaming stores
 };
@@ -696,8 +698,15 @@ DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, const int p
     if (a.in_kind == IN_COMPLEX && a.no_limit) {
         // dense complex rows: element (m, q) of the row at m * 2^LG_M + q
         const V *__restrict__ src = (const V *)a.x + row_in * a.gi.ostride + (((long long)j << LG_M) + q);
+        if (a.seg_shift == 0) {
 #pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = ld_stream(src + c * STEP);
+            for (int c = 0; c < E; ++c) v[c] = ld_stream(src + c * STEP);
+        } else {
+            // segmented rows (the receive buffer of the multi-GPU exchange, [peer][line][part]): a segment is a
+            // whole number of this thread's steps long, so its index depends on c alone
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = ld_stream(src + c * STEP + ((c * STEP) >> a.seg_shift) * a.seg_extra);
+        }
     } else {
         const long long sbase = row_in * a.gi.ostride + (long long)q * a.gi.lstride + (long long)j * a.gi.estride;
         const long long istep = (long long)TT * a.gi.estride;

@@ -656,6 +656,31 @@ int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *ou
                    : run_fft<double, false>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream);
 }
 
+int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, int64_t lines,
+                           int64_t seg_len, int64_t seg_stride, int forward,
+                           void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || !x || !out || lines < 0 || seg_len < 1 || seg_stride < seg_len)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_segmented: bad argument");
+    const long long n = plan->n;
+    const int seg_shift = pow2_shift(seg_len);
+    // only what the multi-GPU four-step needs: two-pass plans, power-of-two segments at least one thread step long
+    const int lg_e1 = plan->dtype == DSC_CUDA_F32 ? pass_lg_e<float>(plan->lg_n1, plan->lg_n2) : pass_lg_e<double>(plan->lg_n1, plan->lg_n2);
+    if (plan->lg_n2 == 0 || seg_shift < 0 || n % seg_len != 0 || seg_len == n || seg_shift < plan->lg_n - lg_e1)
+        return fail(DSC_CUDA_EUNSUPPORTED, "dsc_cuda_fft_segmented: n=%lld with segments of %lld", n, (long long)seg_len);
+    FftArgs a{};
+    a.x = x;
+    a.gi = LineGeom{(long long)seg_len, 1, 1LL << plan->lg_n2};     // line r starts r * seg_len into every segment
+    a.in_limit = n;
+    a.in_kind = IN_COMPLEX;
+    a.seg_shift = seg_shift;
+    a.seg_extra = (long long)(seg_stride - seg_len);
+    if (plan->dtype == DSC_CUDA_F32)
+        return forward ? four_step<float, true>(plan, a, lines, work, work_bytes, out, n, false, stream)
+                       : four_step<float, false>(plan, a, lines, work, work_bytes, out, n, true, stream);
+    return forward ? four_step<double, true>(plan, a, lines, work, work_bytes, out, n, false, stream)
+                   : four_step<double, false>(plan, a, lines, work, work_bytes, out, n, true, stream);
+}
+
 int dsc_cuda_rfft(const dsc_cuda_plan *plan, const void *x, void *out,
                   int64_t outer, int x_n, int64_t inner, void *work, size_t work_bytes, void *stream) {
     if (!plan_ok(plan) || plan->fft_type != DSC_CUDA_FFT_REAL || !x || !out || x_n < 1 || outer < 0 || inner < 1)

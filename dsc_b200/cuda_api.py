@@ -50,6 +50,8 @@ class CudaApi:
         L.dsc_cuda_work_bytes.argtypes = [pp, C.c_int64]
         L.dsc_cuda_fft.argtypes = [pp, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dsc_cuda_fft_segmented.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_rfft.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                     C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_irfft.argtypes = L.dsc_cuda_rfft.argtypes
@@ -87,6 +89,16 @@ class CudaApi:
     def fft(self, plan, x_ptr, x_dtype, out_ptr, outer, x_n, inner, forward, work_ptr=0, work_bytes=0, stream=0):
         self._check(self.lib.dsc_cuda_fft(C.byref(plan), x_ptr, x_dtype, out_ptr, outer, x_n, inner,
                                           int(forward), work_ptr, work_bytes, stream), "dsc_cuda_fft")
+
+    def fft_segmented(self, plan, x_ptr, out_ptr, lines, seg_len, seg_stride, forward, work_ptr=0, work_bytes=0, stream=0):
+        """Lines stored as n/seg_len segments (segment s of line r at x + s*seg_stride + r*seg_len); returns False
+        when this plan / segment size is not covered (caller un-interleaves and uses fft)."""
+        rc = self.lib.dsc_cuda_fft_segmented(C.byref(plan), x_ptr, out_ptr, lines, seg_len, seg_stride, int(forward),
+                                             work_ptr, work_bytes, stream)
+        if rc == -4:         # DSC_CUDA_EUNSUPPORTED
+            return False
+        self._check(rc, "dsc_cuda_fft_segmented")
+        return True
 
     def rfft(self, plan, x_ptr, out_ptr, outer, x_n, inner, work_ptr=0, work_bytes=0, stream=0):
         self._check(self.lib.dsc_cuda_rfft(C.byref(plan), x_ptr, out_ptr, outer, x_n, inner,

@@ -11,7 +11,8 @@ box).  Index split  n = n1*N2 + n2,  k = k1 + N1*k2:
   step 2     : times W_N^{n2 k1} and transpose to [k1][n2_local] (dsc_cuda_transpose_twiddle): the slab
                for peer q, k1 in block q, is then contiguous
   step 3     : all-to-all of the P slabs                    (the ONE exchange; NCCL)
-  step 4     : un-interleave to [k1_local][n2] and N1/P local transforms of length N2
+  step 4     : N1/P local transforms of length N2, read straight from the receive buffer [peer][k1_local][n2_local]
+               (dsc_cuda_fft_segmented; short N2: un-interleave to [k1_local][n2] first)
   layout out : rank p owns k1 in block p: local[k1_local][k2] = X[k1 + N1*k2]   (block-transposed order)
 
 The reference has no counterpart (single process, dsc/src/dsc.cpp:2082-2088 only marks where parallelism
@@ -103,6 +104,12 @@ class ShardedFFT:
         if self.P > 1:
             recv = torch.empty_like(send)                        # [q][k1_local][n2_local]
             dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+            out = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
+            # line k1_local is P segments of N2/P points, one per source rank: transformed where it lies when the
+            # plan is a two-pass one (the first pass reads segmented rows), else un-interleaved first
+            if api.fft_segmented(self.plan2, recv.data_ptr(), out.data_ptr(), self.cols, self.rows,
+                                 self.cols * self.rows, fwd, self.work.data_ptr(), self.work.numel(), s):
+                return out
             b = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
             b.view(self.cols, self.P, self.rows).copy_(recv.view(self.P, self.cols, self.rows).permute(1, 0, 2))
         else:

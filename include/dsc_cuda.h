@@ -84,6 +84,14 @@ int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *ou
                  int64_t outer, int x_n, int64_t inner, int forward,
                  void *work, size_t work_bytes, void *stream);
 
+/* fft / ifft of `lines` complex lines of plan->n points whose storage is SEGMENTED: line r consists of
+ * n / seg_len segments of seg_len contiguous elements, segment s of line r at x + s*seg_stride + r*seg_len
+ * -- the receive buffer [peer][line][part] of the multi-GPU four-step's all-to-all, transformed without
+ * first un-interleaving it.  Two-pass plans only; seg_len a power of two >= n / 32 (float) or n / 16 (double). */
+int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, int64_t lines,
+                           int64_t seg_len, int64_t seg_stride, int forward,
+                           void *work, size_t work_bytes, void *stream);
+
 /* rfft: real (outer, x_n, inner) -> complex (outer, n + 1, inner), plan REAL of order n. */
 int dsc_cuda_rfft(const dsc_cuda_plan *plan, const void *x, void *out,
                   int64_t outer, int x_n, int64_t inner,

@@ -120,6 +120,20 @@ class DevFFT:
         self.api.fft(plan, self.mem.ptr(dx), _CODE[x.dtype], self.mem.ptr(dout), outer, x_n, inner, forward, wp, wb)
         return self.mem.download(dout)
 
+    def fft_segmented(self, segs, forward=True):
+        """segs: [S][lines][seg_len] complex (line r = concatenation of segs[:, r, :]).  Returns [lines][S*seg_len]
+        or None when the library does not cover the shape."""
+        segs = np.ascontiguousarray(segs)
+        S, lines, seg_len = segs.shape
+        n = S * seg_len
+        prec = 0 if segs.dtype == np.complex64 else 1
+        plan = self.plan(n, cuda_api.FFT_COMPLEX, prec)
+        dx = self.mem.upload(segs)
+        dout = self.mem.empty((lines, n), segs.dtype)
+        w, wp, wb = self._work(plan, lines)
+        ok = self.api.fft_segmented(plan, self.mem.ptr(dx), self.mem.ptr(dout), lines, seg_len, lines * seg_len, forward, wp, wb)
+        return self.mem.download(dout) if ok else None
+
     def fft(self, x, n=-1, axis=-1):
         return self._cfft(x, n, axis, True)
 
