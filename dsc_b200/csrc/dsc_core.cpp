@@ -562,12 +562,21 @@ struct xform_job {
     // composed paths (see launch_chunk): two device temporaries and, for huge plans, the sub-plans
     byte *tmp_a, *tmp_b;
     const dsc_fft_plan *sub1, *sub2;
+    usize scratch_capacity;             // bytes of device scratch a launch can use as work memory
 };
 
 #define CUDA_RC(call) do { const int rc_ = (call); if (rc_ != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error()); } while (0)
 
+// complex two-pass transform along a non-last axis that the launch layer runs as ONE launch of column passes
+// (needs a covered shape and a device scratch that holds the work rows of one outer slab; else: transposes)
+bool strided_two_pass_direct(const xform_job &j) noexcept {
+    if (j.plan->huge || j.plan->cu.lg_n2 == 0 || j.inner <= 1 || (j.kind != XF_FFT && j.kind != XF_IFFT)) return false;
+    const usize need = dsc_cuda_work_bytes_axis(&j.plan->cu, 1, j.inner);
+    return need > 0 && need <= j.scratch_capacity;
+}
+
 bool is_composed(const xform_job &j) noexcept {
-    return j.plan->huge || (j.plan->cu.lg_n2 != 0 && j.inner > 1);
+    return j.plan->huge || (j.plan->cu.lg_n2 != 0 && j.inner > 1 && !strided_two_pass_direct(j));
 }
 
 int one_transform(const xform_job &j, const dsc_cuda_plan *plan, const void *src, const int src_dtype, void *dst,
@@ -690,8 +699,15 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
     void *work = nullptr;
     {
         const i64 lines = DSC_MIN(rows_per_chunk, j.outer) * j.inner;
-        const usize need = j.kind == XF_FILTER ? dsc_cuda_filter_work_bytes(&j.plan->cu, lines)
-                                               : dsc_cuda_work_bytes(&j.plan->cu, lines);
+        usize need = j.kind == XF_FILTER ? dsc_cuda_filter_work_bytes(&j.plan->cu, lines)
+                     : strided_two_pass_direct(j) ? dsc_cuda_work_bytes_axis(&j.plan->cu, DSC_MIN(rows_per_chunk, j.outer), j.inner)
+                                                  : dsc_cuda_work_bytes(&j.plan->cu, lines);
+        // long single-pass columns (2^13, 2^14 points along a non-last axis) also run as column passes when the
+        // scratch holds their work rows; without work memory the launch layer uses its single-pass blocks
+        if (need == 0 && j.inner > 1 && !j.plan->huge && (j.kind == XF_FFT || j.kind == XF_IFFT)) {
+            const usize cols = dsc_cuda_work_bytes_axis(&j.plan->cu, DSC_MIN(rows_per_chunk, j.outer), j.inner);
+            if (cols <= ctx->dev_scratch.capacity) need = cols;
+        }
         if (need > 0) {
             // less than `need` still works (the launch layer chunks); one line must fit
             work_bytes = DSC_MIN(need, ctx->dev_scratch.capacity) / DEV_GRANULE * DEV_GRANULE;
@@ -851,6 +867,7 @@ dsc_tensor *dsc_internal_fft(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out,
     out = make_out(ctx, x, out, axis_idx, n, out_dtype);
 
     xform_job j{};
+    j.scratch_capacity = ctx->dev_scratch.capacity;
     j.kind = forward ? XF_FFT : XF_IFFT;
     j.plan = dsc_plan_fft(ctx, n, COMPLEX, out_dtype);
     if (j.plan->huge) {
@@ -897,6 +914,7 @@ dsc_tensor *dsc_internal_rfft(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out
     out = make_out(ctx, x, out, axis_idx, out_n, out_dtype);
 
     xform_job j{};
+    j.scratch_capacity = ctx->dev_scratch.capacity;
     j.kind = forward ? XF_RFFT : XF_IRFFT;
     j.plan = dsc_plan_fft(ctx, order, REAL, x->dtype);
     j.x = x; j.out = out;
@@ -945,6 +963,7 @@ dsc_tensor *dsc_fft_filter(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const
     out = make_out(ctx, x, out, axis_idx, 2 * order, x->dtype);
 
     xform_job j{};
+    j.scratch_capacity = ctx->dev_scratch.capacity;
     j.kind = XF_FILTER;
     j.plan = dsc_plan_fft(ctx, order, REAL, x->dtype);
     j.x = x; j.out = out; j.spectrum = B;

@@ -139,6 +139,47 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
 #define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B>(),
 #define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B>(),
 
+// ---- two-pass transforms along a non-last axis (four_step_columns) --------------------------------------------
+struct ColumnsEntry {
+    void (*fn)(const FftArgs, const FftArgs, const FourStepSync, const ColumnsGeom);
+    int lg_n1, lg_n2, threads, l_a, l_b, smem;
+    int grid;
+    bool configured;
+};
+
+template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_threads<T>(LG_N1, LG_N2)>
+ColumnsEntry make_columns() {
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+    ColumnsEntry e;
+    e.fn = four_step_columns<T, LG_N1, LG_N2, THREADS, FWD>;
+    e.lg_n1 = LG_N1; e.lg_n2 = LG_N2; e.threads = THREADS;
+    e.l_a = THREADS >> (LG_N1 - LG_E1); e.l_b = THREADS >> (LG_N2 - LG_E2);
+    e.smem = fused_smem_bytes<T, LG_N1, LG_N2, THREADS>();
+    e.grid = 0;
+    e.configured = false;
+    return e;
+}
+
+// the fused pairs plus the decompositions of the long single-pass lengths 2^13 and 2^14
+#define DSC_COLUMNS_PAIRS(X) X(7, 6) DSC_FUSED_PAIRS(X)
+
+template <typename T, bool FWD> ColumnsEntry *columns_entry(int lg_n1, int lg_n2);
+template <> ColumnsEntry *columns_entry<float, true>(int, int);
+template <> ColumnsEntry *columns_entry<float, false>(int, int);
+template <> ColumnsEntry *columns_entry<double, true>(int, int);
+template <> ColumnsEntry *columns_entry<double, false>(int, int);
+
+#define DSC_DEFINE_COLUMNS(T, FWD)                                                         \
+    template <> ColumnsEntry *columns_entry<T, FWD>(int lg_n1, int lg_n2) {                \
+        static ColumnsEntry table[] = {DSC_COLUMNS_PAIRS(DSC_COLUMNS_MAKE_##FWD##_##T)};   \
+        for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
+        return nullptr;                                                                    \
+    }
+#define DSC_COLUMNS_MAKE_true_float(A, B) make_columns<float, true, A, B>(),
+#define DSC_COLUMNS_MAKE_false_float(A, B) make_columns<float, false, A, B>(),
+#define DSC_COLUMNS_MAKE_true_double(A, B) make_columns<double, true, A, B>(),
+#define DSC_COLUMNS_MAKE_false_double(A, B) make_columns<double, false, A, B>(),
+
 #define DSC_DEFINE_TABLE(T, FWD, MODE, SV)                                                        \
     template <> KernelEntry *get_table<T, FWD, MODE, SV>() {                                      \
         return build_table<T, FWD, MODE, SV>(std::make_integer_sequence<int, Tile<T>::MAX_LG + 1>{}); \

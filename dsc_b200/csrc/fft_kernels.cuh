@@ -887,14 +887,11 @@ template <typename T, int LG_N1, int LG_N2, int THREADS> __host__ __device__ con
 //     issued its stores of tile i long ago.
 // A flag observed satisfied is followed by a block barrier and then by L2 (.cg) loads of the dependent data,
 // which the producer made visible at L2 before it incremented the flag.
-template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
-four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
-    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
-    constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
-    static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
-    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS>();
-    DSC_DYN_SMEM(smem_raw);
+// The ticket loop of a persistent block.  first(tile, parity, before_scatter) / second(tile, parity,
+// before_scatter) transform one tile of the respective pass and must call before_scatter() exactly once, by
+// every thread, after their last read of the previous tile's shared memory and before their first write.
+template <typename First, typename Second>
+DSC_DEV void run_tickets(const FourStepSync &s, First &&first, Second &&second) {
     __shared__ unsigned ctl_s[2][2];                   // [parity]{ticket, dependency already satisfied}
     const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
     unsigned pending = 0;                              // thread 0: ticket of the tile after the next one
@@ -946,12 +943,132 @@ four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
             __syncthreads();                                                          // W
             if (threadIdx.x == 0 && prev_done != nullptr) dsc_signal_release(prev_done);
         };
-        if (role_a) pass_first_tile<T, LG_N1, LG_N2, LG_E1, LPB_A, TABLE_AT, FWD>(a, (long long)row * s.tiles_a + r, par, smem_raw, before_scatter);
-        else pass_second_tile<T, LG_N2, LG_N1, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw, before_scatter);
+        if (role_a) first(row, r, par, before_scatter);
+        else second(row, r, par, before_scatter);
         prev_done = (role_a ? s.a_done : s.b_done) + row;
     }
     __syncthreads();
     if (threadIdx.x == 0 && prev_done != nullptr) dsc_signal_release(prev_done);
+}
+
+template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+    constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
+    static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
+    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS>();
+    DSC_DYN_SMEM(smem_raw);
+    run_tickets(s,
+        [&](unsigned row, unsigned r, int par, auto &before_scatter) {
+            pass_first_tile<T, LG_N1, LG_N2, LG_E1, LPB_A, TABLE_AT, FWD>(a, (long long)row * s.tiles_a + r, par, smem_raw, before_scatter);
+        },
+        [&](unsigned row, unsigned r, int, auto &before_scatter) {
+            pass_second_tile<T, LG_N2, LG_N1, LG_E2, LPB_B, FWD>(b, (long long)row * s.tiles_b + r, smem_raw, before_scatter);
+        });
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-pass transforms along a NON-last axis: both passes are column passes.
+//
+// The tensor is (outer, n, inner), n = n1*n2, i = i1*n2 + i2.  The inner extent is cut into chunks of Ic
+// columns; a "row" of the launch is one (outer, chunk) pair, n x Ic points, small enough for its intermediate
+// to stay in L2.  A tile is L adjacent columns (adjacent lanes on adjacent columns: L*sizeof(V) contiguous
+// bytes per position on both global sides) at a fixed i2 (first pass) or k1 (second pass):
+//   first pass   over i1 at stride n2*inner, times W_n^(i2 k1) -- i2 is one number per tile, so the twiddle
+//                is W^(i2 j) per thread times a table of E powers per tile -- into work[k1][i2][Ic];
+//   second pass  over i2 at stride Ic of the work row, out at (k1 + n1 k2)*inner.
+struct ColumnsGeom {
+    long long x_ostride, out_ostride;     // elements between outer slabs of the source / the destination
+    long long inner;                      // elements between consecutive points of a column
+    int lg_ic, chunks;                    // chunk width (log2) and chunks per outer slab
+    int x_n;                              // valid points per source column (pad / crop)
+    int x_real;                           // source holds T, not cx<T>
+};
+
+template <typename T, int LG_N, int LG_M, int LG_E, int L, int TABLE_AT, bool FWD, bool FIRST, typename Hook>
+DSC_DEV void column_tile(const FftArgs &a, const ColumnsGeom &g, const unsigned row, const unsigned tile, const int parity,
+                         unsigned char *smem_raw, Hook &&before_scatter) {
+    using Sc = Sched<LG_N, LG_E>;
+    using V = cx<T>;
+    using PT = PassTile<T, LG_N, LG_E, L>;
+    constexpr int E = Sc::E, TT = Sc::TT, THREADS = L * TT;
+    static_assert(Sc::STAGES >= 2, "the twiddle table is published by the first exchange barrier");
+    V *sm_all = (V *)smem_raw;
+    const int tid = threadIdx.x, l = tid % L, j = tid / L;
+    V *sm = sm_all + PT::line_base(l);
+    V *tw_c = sm_all + TABLE_AT + parity * E;
+    const LineSync ls{SYNC_BLOCK, 0, THREADS};
+
+    const unsigned per = (1u << g.lg_ic) / L;                 // tiles per fixed index (i2 or k1)
+    const unsigned fixed = tile / per, col0 = (tile % per) * L;
+    const unsigned o = row / (unsigned)g.chunks, ch = row % (unsigned)g.chunks;
+    const long long ring_row_in = a.ring_in ? row % a.ring_in : row;
+    const long long ring_row_out = a.ring_out ? row % a.ring_out : row;
+    const long long row_elems = (long long)1 << (LG_N + LG_M + g.lg_ic);
+
+    V v[E];
+    if (FIRST) {
+        // source column (i2 = fixed): point i1 = j + c TT at i = i1 n2 + i2
+        const long long base = (long long)o * g.x_ostride + ((long long)ch << g.lg_ic) + col0 + l;
+        const V zero = mk<T>((T)0, (T)0);
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const long long i = ((long long)(j + c * TT) << LG_M) + fixed;
+            const long long off = base + i * g.inner;
+            if (i >= g.x_n) v[c] = zero;
+            else if (g.x_real) v[c] = mk<T>(__ldcs((const T *)a.x + off), (T)0);
+            else v[c] = ld_stream((const V *)a.x + off);
+        }
+        if (tid < E) tw_c[tid] = four_step_twiddle<T>(a, fixed * (unsigned)TT * (unsigned)tid);
+    } else {
+        // work row [k1 = fixed][i2][Ic]: point i2 = j + c TT
+        const V *__restrict__ src = (const V *)a.x + ring_row_in * row_elems +
+                                    ((((long long)fixed << LG_N) + j) << g.lg_ic) + col0 + l;
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = __ldcg(src + ((long long)(c * TT) << g.lg_ic));
+    }
+
+    Stage<T, LG_N, LG_E, FWD, 0>::run(v, sm, j, sm, j, a, ls, before_scatter);
+
+    if (FIRST) {
+        const V w0 = four_step_twiddle<T>(a, fixed * (unsigned)j);
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], c == 0 ? w0 : cmul(w0, tw_c[c]));
+        // work[k1 = j + c TT][i2 = fixed][Ic]
+        V *__restrict__ op = (V *)a.out + ring_row_out * row_elems + ((((long long)j << LG_M) + fixed) << g.lg_ic) + col0 + l;
+#pragma unroll
+        for (int c = 0; c < E; ++c) op[(long long)(c * TT) << (LG_M + g.lg_ic)] = v[c];
+    } else {
+        if (a.do_scale) {
+            const T sc = (T)a.scale;
+#pragma unroll
+            for (int c = 0; c < E; ++c) { v[c].x *= sc; v[c].y *= sc; }
+        }
+        // X[k1 + n1 k2], k2 = j + c TT
+        V *__restrict__ op = (V *)a.out + (long long)o * g.out_ostride + ((long long)ch << g.lg_ic) + col0 + l;
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+            const long long k = (long long)fixed + ((long long)(j + c * TT) << LG_M);
+            __stcs(op + k * g.inner, v[c]);
+        }
+    }
+}
+
+template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+four_step_columns(const FftArgs a, const FftArgs b, const FourStepSync s, const ColumnsGeom g) {
+    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+    constexpr int L_A = THREADS >> (LG_N1 - LG_E1), L_B = THREADS >> (LG_N2 - LG_E2);
+    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS>();
+    DSC_DYN_SMEM(smem_raw);
+    run_tickets(s,
+        [&](unsigned row, unsigned r, int par, auto &before_scatter) {
+            column_tile<T, LG_N1, LG_N2, LG_E1, L_A, TABLE_AT, FWD, true>(a, g, row, r, par, smem_raw, before_scatter);
+        },
+        [&](unsigned row, unsigned r, int par, auto &before_scatter) {
+            column_tile<T, LG_N2, LG_N1, LG_E2, L_B, TABLE_AT, FWD, false>(b, g, row, r, par, smem_raw, before_scatter);
+        });
 }
 
 // Large packed-real transforms (order N beyond one shared-memory pass): the same bin-pair

@@ -64,8 +64,14 @@ struct PlanLayout {
     int lg_n, lg_n1, lg_n2, four_shift, real_shift, lg_e1, lg_e2;
     size_t off_tw1[DSC_CUDA_MAX_STAGES], off_tw2[DSC_CUDA_MAX_STAGES];
     size_t off_lo, off_hi, off_real, off_real_lo, off_real_hi, total;
+    // column decomposition of long single-pass complex plans (transforms along a non-last axis)
+    int col_lg_n1, col_lg_n2, col_shift, col_lg_e1, col_lg_e2;
+    size_t off_ctw1[DSC_CUDA_MAX_STAGES], off_ctw2[DSC_CUDA_MAX_STAGES], off_clo, off_chi;
     bool ok;
 };
+
+// shortest single-pass length (log2) that also gets a column decomposition
+template <typename T> constexpr int columns_min_lg() { return 13; }
 
 template <typename T> PlanLayout plan_layout(int n, int fft_type) {
     PlanLayout L{};
@@ -91,6 +97,18 @@ template <typename T> PlanLayout plan_layout(int n, int fft_type) {
         L.four_shift = (L.lg_n + 1) / 2;
         L.off_lo = take((size_t)1 << L.four_shift);
         L.off_hi = take((size_t)1 << (L.lg_n - L.four_shift));
+    }
+    if (L.lg_n2 == 0 && fft_type == DSC_CUDA_FFT_COMPLEX && L.lg_n >= columns_min_lg<T>()) {
+        L.col_lg_n2 = L.lg_n / 2;
+        L.col_lg_n1 = L.lg_n - L.col_lg_n2;
+        L.col_lg_e1 = pass_lg_e<T>(L.col_lg_n1, L.col_lg_n2);
+        L.col_lg_e2 = pass_lg_e<T>(L.col_lg_n2, L.col_lg_n1);
+        const SubSched c1 = sub_sched(L.col_lg_n1, L.col_lg_e1), c2 = sub_sched(L.col_lg_n2, L.col_lg_e2);
+        for (int s = 1; s < c1.stages; ++s) L.off_ctw1[s] = take((size_t)(c1.r[s] - 1) * c1.ns[s]);
+        for (int s = 1; s < c2.stages; ++s) L.off_ctw2[s] = take((size_t)(c2.r[s] - 1) * c2.ns[s]);
+        L.col_shift = (L.lg_n + 1) / 2;
+        L.off_clo = take((size_t)1 << L.col_shift);
+        L.off_chi = take((size_t)1 << (L.lg_n - L.col_shift));
     }
     if (fft_type == DSC_CUDA_FFT_REAL) {
         if (L.lg_n2 == 0) L.off_real = take((size_t)n / 2 + 1);
@@ -133,6 +151,21 @@ int build_tables(dsc_cuda_plan *p, const PlanLayout &L, void *stream) {
         p->tw_hi = base + L.off_hi;
         fill_pow(p->tw_lo, 1LL << L.four_shift, 1, n);
         fill_pow(p->tw_hi, 1LL << (L.lg_n - L.four_shift), 1LL << L.four_shift, n);
+    }
+    if (L.lg_n2) {
+        // a two-pass plan is its own column decomposition
+        p->col_lg_n1 = L.lg_n1; p->col_lg_n2 = L.lg_n2; p->col_shift = L.four_shift;
+        for (int s = 0; s < DSC_CUDA_MAX_STAGES; ++s) { p->col_tw1[s] = p->tw1[s]; p->col_tw2[s] = p->tw2[s]; }
+        p->col_lo = p->tw_lo; p->col_hi = p->tw_hi;
+    } else if (L.col_lg_n2) {
+        p->col_lg_n1 = L.col_lg_n1; p->col_lg_n2 = L.col_lg_n2; p->col_shift = L.col_shift;
+        const SubSched c1 = sub_sched(L.col_lg_n1, L.col_lg_e1), c2 = sub_sched(L.col_lg_n2, L.col_lg_e2);
+        for (int s = 1; s < c1.stages; ++s) { p->col_tw1[s] = base + L.off_ctw1[s]; fill_stage(p->col_tw1[s], c1.ns[s], c1.r[s]); }
+        for (int s = 1; s < c2.stages; ++s) { p->col_tw2[s] = base + L.off_ctw2[s]; fill_stage(p->col_tw2[s], c2.ns[s], c2.r[s]); }
+        p->col_lo = base + L.off_clo;
+        p->col_hi = base + L.off_chi;
+        fill_pow(p->col_lo, 1LL << L.col_shift, 1, n);
+        fill_pow(p->col_hi, 1LL << (L.lg_n - L.col_shift), 1LL << L.col_shift, n);
     }
     if (p->fft_type == DSC_CUDA_FFT_REAL) {
         if (L.lg_n2 == 0) {
@@ -348,6 +381,100 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
     return 0;
 }
 
+// chunk width (log2) of the column launch: rows of n x Ic points of about 4 MiB, at least one tile wide
+inline int columns_chunk_lg(long long n, int lg_inner, int l_max, size_t elem_bytes) {
+    int lg_ic = lg_inner;
+    while ((1LL << lg_ic) > l_max && ((size_t)n << lg_ic) * elem_bytes > ((size_t)4 << 20)) --lg_ic;
+    return lg_ic;
+}
+
+// Two-pass transform along a non-last axis of a contiguous (outer, x_n, inner) tensor, inner a power of two wide
+// enough for a tile: ONE persistent launch whose two passes are both column passes (four_step_columns).
+// Returns DSC_CUDA_EUNSUPPORTED when the shape is not covered (the tensor layer then composes transposes).
+template <typename T, bool FWD>
+int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real, void *out, long long outer, int x_n,
+                             long long inner, void *work, size_t work_bytes, void *stream) {
+    using V = cx<T>;
+    const long long n = p->n;
+    ColumnsEntry *ce = p->col_lg_n2 ? columns_entry<T, FWD>(p->col_lg_n1, p->col_lg_n2) : nullptr;
+    const int lg_inner = pow2_shift(inner);
+    if (ce == nullptr || lg_inner < 0) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis of inner extent %lld", n, inner);
+    const int l_max = ce->l_a > ce->l_b ? ce->l_a : ce->l_b;
+    if (inner < l_max) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld): inner extent %lld is narrower than a tile", n, inner);
+    const int lg_ic = columns_chunk_lg(n, lg_inner, l_max, sizeof(V));
+    const long long ic = 1LL << lg_ic, chunks = inner >> lg_ic, rows = outer * chunks;
+    if (rows <= 0) return 0;
+    const size_t row_bytes = (size_t)n * (size_t)ic * sizeof(V);
+    const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
+    const long long tiles_a = (1LL << p->col_lg_n2) * (ic / ce->l_a), tiles_b = (1LL << p->col_lg_n1) * (ic / ce->l_b);
+    if (work == nullptr || work_bytes < sync_bytes + row_bytes || rows * (tiles_a + tiles_b) >= 0x7fffffffLL ||
+        outer * chunks > 0x7fffffffLL)
+        return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis: work buffer of %zu bytes holds no row of %zu", n, work_bytes, row_bytes);
+#if defined(DSC_EMUL)
+    ce->grid = 3;
+#else
+    if (!ce->configured) {
+        if (ce->smem > 48 * 1024) {
+            const cudaError_t err = cudaFuncSetAttribute((const void *)ce->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce->smem);
+            if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
+        }
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ce->fn, ce->threads, ce->smem);
+        if (err == cudaSuccess) err = cudaGetDevice(&dev);
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess || per_sm < 1) return fail(DSC_CUDA_ELAUNCH, "occupancy query: %s", cudaGetErrorString(err));
+        ce->grid = per_sm * sms;
+        ce->configured = true;
+    }
+#endif
+    long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
+    const long long cap = (long long)(((size_t)64 << 20) / row_bytes) > 4 ? (long long)(((size_t)64 << 20) / row_bytes) : 4;
+    if (ring > cap) ring = cap;
+    if (ring >= rows) ring = 0;
+    FourStepSync s{};
+    s.ticket = (unsigned *)work;
+    s.a_done = s.ticket + 1;
+    s.b_done = s.a_done + rows;
+    s.tiles_a = (int)tiles_a;
+    s.tiles_b = (int)tiles_b;
+    s.ring = (int)ring;
+    s.rows = (int)rows;
+    long long lag = (3LL * ce->grid + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
+    if (lag < 1) lag = 1;
+    if (ring > 0 && lag > ring / 2) lag = ring / 2;
+    if (lag < 1) lag = 1;
+    if (lag > rows) lag = rows;
+    s.lag = (int)lag;
+
+    V *mid = (V *)((char *)work + sync_bytes);
+    FftArgs a{}, b{};
+    a.x = x; a.out = mid; a.ring_out = ring;
+    set_stage_tables<T>(a, p->col_tw1);
+    a.tw_lo = p->col_lo; a.tw_hi = p->col_hi;
+    a.four_shift = p->col_shift; a.four_mask = (1 << p->col_shift) - 1;
+    b.x = mid; b.out = out; b.ring_in = ring;
+    set_stage_tables<T>(b, p->col_tw2);
+    b.do_scale = !FWD; b.scale = 1.0 / (double)n;
+    ColumnsGeom g{};
+    g.x_ostride = (long long)x_n * inner;
+    g.out_ostride = n * inner;
+    g.inner = inner;
+    g.lg_ic = lg_ic;
+    g.chunks = (int)chunks;
+    g.x_n = x_n < n ? x_n : (int)n;
+    g.x_real = x_real;
+#if defined(DSC_EMUL)
+    memset(work, 0, sync_bytes);
+#else
+    const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
+    if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
+#endif
+    const long long tiles = rows * (tiles_a + tiles_b);
+    const unsigned blocks = (unsigned)(tiles < ce->grid ? tiles : ce->grid);
+    DSC_LAUNCH(ce->fn, blocks, ce->threads, ce->smem, stream, a, b, s, g);
+    return check_launch("four_step_columns");
+}
+
 template <typename T, bool FWD>
 int run_fft(const dsc_cuda_plan *p, const void *x, bool x_real, void *out,
             long long outer, int x_n, long long inner, void *work, size_t work_bytes, void *stream) {
@@ -369,9 +496,14 @@ int run_fft(const dsc_cuda_plan *p, const void *x, bool x_real, void *out,
         KernelEntry *fast = get_table<T, FWD, MODE_FAST, false>();
         if (inner == 1 && !x_real && x_n == n && a.lines % fast[p->lg_n].lpb == 0)
             return launch_lines(fast, p->lg_n, a, stream);
+        // long columns: both passes of the plan's column decomposition in one launch (whole 64-512-byte
+        // segments per access instead of the 8-16 bytes per column a single-pass block of this length touches)
+        if (inner > 1 && p->col_lg_n2 != 0 && work != nullptr &&
+            four_step_columns_launch<T, FWD>(p, x, x_real, out, outer, x_n, inner, work, work_bytes, stream) == 0)
+            return 0;
         return launch_lines(c2c_table<T, FWD>(inner > 1), p->lg_n, a, stream);
     }
-    if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis", n);
+    if (inner != 1) return four_step_columns_launch<T, FWD>(p, x, x_real, out, outer, x_n, inner, work, work_bytes, stream);
     FftArgs a{};
     a.x = x;
     a.gi = LineGeom{(long long)x_n, 1, 1LL << p->lg_n2};
@@ -640,6 +772,25 @@ size_t dsc_cuda_work_bytes(const dsc_cuda_plan *plan, int64_t lines) {
     size_t total = sync + ring * row + 256;
     if (plan->fft_type == DSC_CUDA_FFT_REAL) total = 2 * total + 4096;
     return total;
+}
+
+size_t dsc_cuda_work_bytes_axis(const dsc_cuda_plan *plan, int64_t outer, int64_t inner) {
+    if (inner <= 1) return dsc_cuda_work_bytes(plan, outer);
+    if (!plan_ok(plan) || plan->col_lg_n2 == 0 || outer <= 0) return 0;
+    const bool f32 = plan->dtype == DSC_CUDA_F32;
+    ColumnsEntry *ce = f32 ? columns_entry<float, true>(plan->col_lg_n1, plan->col_lg_n2)
+                           : columns_entry<double, true>(plan->col_lg_n1, plan->col_lg_n2);
+    const int lg_inner = pow2_shift(inner);
+    if (ce == nullptr || lg_inner < 0) return 0;
+    const int l_max = ce->l_a > ce->l_b ? ce->l_a : ce->l_b;
+    if (inner < l_max) return 0;
+    const size_t es = f32 ? sizeof(float2) : sizeof(double2);
+    const int lg_ic = columns_chunk_lg(plan->n, lg_inner, l_max, es);
+    const size_t rows = (size_t)outer * (size_t)(inner >> lg_ic);
+    const size_t row = ((size_t)plan->n << lg_ic) * es;
+    size_t ring = ((size_t)64 << 20) / row > 4 ? ((size_t)64 << 20) / row : 4;
+    if (ring > rows) ring = rows;
+    return align_up((1 + 2 * rows) * sizeof(unsigned), 256) + ring * row + 256;
 }
 
 int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *out,

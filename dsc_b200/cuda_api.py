@@ -24,7 +24,10 @@ class Plan(C.Structure):
                 ("dev_base", C.c_void_p), ("dev_bytes", C.c_size_t),
                 ("tw1", C.c_void_p * MAX_STAGES), ("tw2", C.c_void_p * MAX_STAGES),
                 ("tw_lo", C.c_void_p), ("tw_hi", C.c_void_p), ("tw_real", C.c_void_p),
-                ("tw_real_lo", C.c_void_p), ("tw_real_hi", C.c_void_p), ("real_shift", C.c_int)]
+                ("tw_real_lo", C.c_void_p), ("tw_real_hi", C.c_void_p), ("real_shift", C.c_int),
+                ("col_lg_n1", C.c_int), ("col_lg_n2", C.c_int), ("col_shift", C.c_int),
+                ("col_tw1", C.c_void_p * MAX_STAGES), ("col_tw2", C.c_void_p * MAX_STAGES),
+                ("col_lo", C.c_void_p), ("col_hi", C.c_void_p)]
 
 
 class DscCudaError(RuntimeError):
@@ -48,6 +51,8 @@ class CudaApi:
         L.dsc_cuda_plan_build.argtypes = [pp, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_work_bytes.restype = C.c_size_t
         L.dsc_cuda_work_bytes.argtypes = [pp, C.c_int64]
+        L.dsc_cuda_work_bytes_axis.restype = C.c_size_t
+        L.dsc_cuda_work_bytes_axis.argtypes = [pp, C.c_int64, C.c_int64]
         L.dsc_cuda_fft.argtypes = [pp, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_fft_segmented.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
@@ -85,6 +90,9 @@ class CudaApi:
 
     def work_bytes(self, plan: Plan, lines: int) -> int:
         return self.lib.dsc_cuda_work_bytes(C.byref(plan), lines)
+
+    def work_bytes_axis(self, plan: Plan, outer: int, inner: int) -> int:
+        return self.lib.dsc_cuda_work_bytes_axis(C.byref(plan), outer, inner)
 
     def fft(self, plan, x_ptr, x_dtype, out_ptr, outer, x_n, inner, forward, work_ptr=0, work_bytes=0, stream=0):
         self._check(self.lib.dsc_cuda_fft(C.byref(plan), x_ptr, x_dtype, out_ptr, outer, x_n, inner,

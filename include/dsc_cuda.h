@@ -60,6 +60,13 @@ typedef struct dsc_cuda_plan {
     void *tw_real;              /* REAL plans, single pass: W_2n^k, k <= n/2 */
     void *tw_real_lo, *tw_real_hi;  /* REAL plans, two-pass: W_2n^p split the same way */
     int real_shift;
+    /* Transforms along a NON-last axis run both passes of a two-pass decomposition as column passes.  Two-pass
+     * plans reuse their own tables (the col_* fields alias them); single-pass COMPLEX plans of >= 2^13 points,
+     * whose strided single-pass blocks would only touch 8-16 contiguous bytes per column, carry these extra
+     * tables.  col_lg_n2 == 0: no column decomposition. */
+    int col_lg_n1, col_lg_n2, col_shift;
+    void *col_tw1[DSC_CUDA_MAX_STAGES], *col_tw2[DSC_CUDA_MAX_STAGES];
+    void *col_lo, *col_hi;
 } dsc_cuda_plan;
 
 const char *dsc_cuda_last_error(void);
@@ -76,6 +83,12 @@ int dsc_cuda_plan_build(dsc_cuda_plan *plan, int n, int fft_type, int dtype,
  * Any smaller non-zero amount that holds at least one line also works: the launch is
  * chunked.  Two-pass plans keep their intermediate here so it can stay L2-resident. */
 size_t dsc_cuda_work_bytes(const dsc_cuda_plan *plan, int64_t lines);
+
+/* The same for a transform along the middle axis of (outer, n, inner): for inner > 1 two-pass plans run both
+ * passes as column passes over chunks of the inner extent and keep the chunk's intermediate here.  0 when the
+ * shape is not covered (inner not a power of two or narrower than a tile): dsc_cuda_fft then reports
+ * DSC_CUDA_EUNSUPPORTED and the caller transposes. */
+size_t dsc_cuda_work_bytes_axis(const dsc_cuda_plan *plan, int64_t outer, int64_t inner);
 
 /* fft / ifft along the middle axis of a contiguous (outer, x_n, inner) tensor.
  * x_dtype in {F32,F64,C32,C64}; out is complex of the plan's precision with extent plan->n

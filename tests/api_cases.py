@@ -253,6 +253,12 @@ def check_composed_paths(dsc):
     x = randn(rng, (1 << 15, 3), "complex64")
     got = dsc.fft(x, axis=0).numpy()
     assert rel_l2(got, port.fft(x, axis=0)) < 1e-6
+    # ... and as ONE launch of two column passes when the inner extent is a power of two wide enough for a tile
+    xw = randn(rng, (2, 1 << 15, 64), "complex64")
+    yw = dsc.fft(xw, axis=1)
+    assert rel_l2(yw.numpy(), port.fft(xw, axis=1)) < 1e-6
+    assert rel_l2(dsc.ifft(yw, axis=-2).numpy(), xw) < 1e-6
+    del yw
     xr = randn(rng, (2, 1 << 16, 2), "float32")
     X = dsc.rfft(xr, axis=1)
     want = port.rfft(xr, -1, 1)

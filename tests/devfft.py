@@ -116,7 +116,12 @@ class DevFFT:
         shape = list(x.shape); shape[ax] = fft_n
         dx = self.mem.upload(x)
         dout = self.mem.empty(shape, _CPLX[x.dtype])
-        w, wp, wb = self._work(plan, outer * inner)
+        if inner > 1 and plan.col_lg_n2:
+            nbytes = self.api.work_bytes_axis(plan, outer, inner)
+            w = self.mem.alloc(nbytes) if nbytes else None
+            wp, wb = (self.mem.ptr(w), nbytes) if nbytes else (0, 0)
+        else:
+            w, wp, wb = self._work(plan, outer * inner)
         self.api.fft(plan, self.mem.ptr(dx), _CODE[x.dtype], self.mem.ptr(dout), outer, x_n, inner, forward, wp, wb)
         return self.mem.download(dout)
 

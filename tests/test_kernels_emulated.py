@@ -182,6 +182,26 @@ def test_two_pass_segmented_rows(dev, dtype, lg, segs):
     assert dev.fft_segmented(parts[:, :, :64].copy()) is None      # single-pass length: not covered, caller copies
 
 
+@pytest.mark.parametrize("dtype,lg,outer,inner", [("complex64", 15, 2, 64), ("complex64", 16, 1, 64),
+                                                   ("complex128", 14, 2, 32), ("complex128", 15, 1, 32),
+                                                   ("complex64", 13, 2, 128), ("complex64", 14, 1, 64),
+                                                   ("complex128", 13, 1, 64)])
+def test_two_pass_along_strided_axis(dev, dtype, lg, outer, inner):
+    """Long columns (a NON-last axis): one launch, both passes of a two-pass decomposition as column tiles --
+    lengths beyond one shared-memory pass, and the single-pass lengths 2^13 / 2^14 whose plans carry a column
+    decomposition as well."""
+    rng = np.random.default_rng(lg + inner)
+    n = 1 << lg
+    x = randn(rng, (outer, n, inner), dtype)
+    y = dev.fft(x, axis=1)
+    assert rel_l2(y, port.fft(x, axis=1)) < TIGHT[dtype]
+    assert rel_l2(dev.ifft(y, axis=1), x) < TIGHT[dtype]
+    xs = x[:, : n - 300, :]                              # zero-padded columns, and real input cast
+    assert rel_l2(dev.fft(xs, n=n, axis=1), port.fft(xs, n=n, axis=1)) < TIGHT[dtype]
+    xr = np.ascontiguousarray(xs.real)
+    assert rel_l2(dev.fft(xr, n=n, axis=1), port.fft(xr, n=n, axis=1)) < TIGHT[dtype]
+
+
 def test_two_pass_chunked_work_buffer():
     d = DevFFT(os.path.join(EMUL_DIR, "libdsc_emul.so"), work_lines=2)
     rng = np.random.default_rng(3)

@@ -18,12 +18,14 @@ def run(outer, n, inner, prec=0, reps=5):
     pm = torch.empty(nb, dtype=torch.uint8, device=dev)
     plan = api.plan_build(n, cuda_api.FFT_COMPLEX, prec, pm.data_ptr(), nb)
     code = 2 if prec == 0 else 3
+    wb = api.work_bytes_axis(plan, outer, inner)
+    work = torch.empty(max(wb, 16), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(reps):
         if i == 1:
             e0.record()
-        api.fft(plan, x.data_ptr(), code, y.data_ptr(), outer, n, inner, True, 0, 0)
+        api.fft(plan, x.data_ptr(), code, y.data_ptr(), outer, n, inner, True, work.data_ptr(), wb)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps - 1)
@@ -36,5 +38,8 @@ def run(outer, n, inner, prec=0, reps=5):
 for shape in [(1, 4096, 32768), (32, 4096, 1024), (1, 1024, 131072), (128, 1024, 1024), (2048, 256, 256),
               (1, 64, 2097152), (1, 8192, 16384), (1, 16384, 8192), (32768, 64, 64), (1048576, 16, 8), (4096, 4096, 3)]:
     run(*shape)
+for shape in [(1, 32768, 4096), (4, 65536, 512), (1, 1 << 20, 128), (16, 32768, 256)]:
+    run(*shape)
 run(1, 4096, 16384, 1)
+run(1, 16384, 4096, 1)
 run(64, 1024, 1024, 1)
