@@ -984,6 +984,13 @@ struct ColumnsGeom {
     int lg_ic, chunks;                    // chunk width (log2) and chunks per outer slab
     int x_n;                              // valid points per source column (pad / crop)
     int x_real;                           // source holds T, not cx<T>
+    // optional output twiddle of the second pass: out[k][col] *= W_M^((col_offset + col) k), M = post_mask + 1, looked
+    // up through the second-pass FftArgs' tw_lo / tw_hi split tables.  This is the inter-pass twiddle of an OUTER
+    // four-step whose columns are spread over several GPUs (the multi-GPU transform): the launch then delivers
+    // the twiddled, k-major matrix that goes straight into the all-to-all.
+    int post_twiddle;
+    unsigned post_mask;
+    long long col_offset;
 };
 
 template <typename T, int LG_N, int LG_M, int LG_E, int L, int TABLE_AT, bool FWD, bool FIRST, typename Hook>
@@ -1044,6 +1051,38 @@ DSC_DEV void column_tile(const FftArgs &a, const ColumnsGeom &g, const unsigned 
             const T sc = (T)a.scale;
 #pragma unroll
             for (int c = 0; c < E; ++c) { v[c].x *= sc; v[c].y *= sc; }
+        }
+        if (g.post_twiddle) {
+            // exponent (col) * k, k = fixed + (j + c TT) 2^LG_M: a base per thread times the c-th power of one ratio,
+            // built from the ratio's 1st, 2nd, 4th, ... powers (each one table lookup, <= log2(E) - 1 products deep)
+            const unsigned col = (unsigned)(g.col_offset + ((long long)ch << g.lg_ic) + col0 + l);
+            const unsigned k0 = (unsigned)fixed + ((unsigned)j << LG_M);
+            // w_c = base * ratio^c with c = 4 a + b:  (base * ratio^(4a)) * ratio^b -- E/4 + 3 values in registers, each
+            // at most three products deep from table lookups of base, ratio^1, ^2, ^4, ^8, ^16
+            constexpr int GROUPS = E / 4;
+            static_assert(E >= 4 && GROUPS <= 8, "column tiles hold 16 or 32 points per thread");
+            auto ratio_pow = [&](const int e) { return four_step_twiddle<T>(a, (col * ((unsigned)(e * TT) << LG_M)) & g.post_mask); };
+            V hi4[GROUPS], lo3[4];
+            hi4[0] = four_step_twiddle<T>(a, (col * k0) & g.post_mask);
+            lo3[1] = ratio_pow(1);
+            lo3[2] = ratio_pow(2);
+            lo3[3] = cmul(lo3[1], lo3[2]);
+            const V r4 = ratio_pow(4);
+            hi4[1] = cmul(hi4[0], r4);
+            if constexpr (GROUPS > 2) {
+                const V r8 = ratio_pow(8);
+                hi4[2] = cmul(hi4[0], r8);
+                hi4[3] = cmul(hi4[2], r4);
+                if constexpr (GROUPS > 4) {
+                    const V r16 = ratio_pow(16);
+                    hi4[4] = cmul(hi4[0], r16);
+                    hi4[5] = cmul(hi4[4], r4);
+                    hi4[6] = cmul(hi4[4], r8);
+                    hi4[7] = cmul(hi4[6], r4);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], (c & 3) == 0 ? hi4[c >> 2] : cmul(hi4[c >> 2], lo3[c & 3]));
         }
         // X[k1 + n1 k2], k2 = j + c TT
         V *__restrict__ op = (V *)a.out + (long long)o * g.out_ostride + ((long long)ch << g.lg_ic) + col0 + l;

@@ -391,9 +391,16 @@ inline int columns_chunk_lg(long long n, int lg_inner, int l_max, size_t elem_by
 // Two-pass transform along a non-last axis of a contiguous (outer, x_n, inner) tensor, inner a power of two wide
 // enough for a tile: ONE persistent launch whose two passes are both column passes (four_step_columns).
 // Returns DSC_CUDA_EUNSUPPORTED when the shape is not covered (the tensor layer then composes transposes).
+struct PostTwiddle {            // optional output twiddle of the column launch (ColumnsGeom::post_twiddle)
+    const void *lo, *hi;
+    int shift;
+    long long total, col_offset;
+};
+
 template <typename T, bool FWD>
 int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real, void *out, long long outer, int x_n,
-                             long long inner, void *work, size_t work_bytes, void *stream) {
+                             long long inner, void *work, size_t work_bytes, void *stream,
+                             const PostTwiddle *post = nullptr) {
     using V = cx<T>;
     const long long n = p->n;
     ColumnsEntry *ce = p->col_lg_n2 ? columns_entry<T, FWD>(p->col_lg_n1, p->col_lg_n2) : nullptr;
@@ -463,6 +470,13 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     g.chunks = (int)chunks;
     g.x_n = x_n < n ? x_n : (int)n;
     g.x_real = x_real;
+    if (post != nullptr) {
+        g.post_twiddle = 1;
+        g.post_mask = (unsigned)(post->total - 1);
+        g.col_offset = post->col_offset;
+        b.tw_lo = post->lo; b.tw_hi = post->hi;
+        b.four_shift = post->shift; b.four_mask = (1 << post->shift) - 1;
+    }
 #if defined(DSC_EMUL)
     memset(work, 0, sync_bytes);
 #else
@@ -805,6 +819,19 @@ int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *ou
                        : run_fft<float, false>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream);
     return forward ? run_fft<double, true>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream)
                    : run_fft<double, false>(plan, x, x_real, out, outer, x_n, inner, work, work_bytes, stream);
+}
+
+int dsc_cuda_fft_columns_twiddled(const dsc_cuda_plan *plan, const void *x, void *out, int64_t cols, int forward,
+                                  int64_t col_offset, const void *tw_lo, const void *tw_hi, int shift, int64_t total,
+                                  void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || !x || !out || cols < 1 || !tw_lo || !tw_hi || total < 1 || (total & (total - 1)) || total > (1LL << 31))
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_columns_twiddled: bad argument");
+    PostTwiddle post{tw_lo, tw_hi, shift, (long long)total, (long long)col_offset};
+    if (plan->dtype == DSC_CUDA_F32)
+        return forward ? four_step_columns_launch<float, true>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post)
+                       : four_step_columns_launch<float, false>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post);
+    return forward ? four_step_columns_launch<double, true>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post)
+                   : four_step_columns_launch<double, false>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post);
 }
 
 int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, int64_t lines,

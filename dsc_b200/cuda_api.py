@@ -57,6 +57,8 @@ class CudaApi:
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_fft_segmented.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                              C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dsc_cuda_fft_columns_twiddled.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p,
+                                                    C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_rfft.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                     C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_irfft.argtypes = L.dsc_cuda_rfft.argtypes
@@ -106,6 +108,17 @@ class CudaApi:
         if rc == -4:         # DSC_CUDA_EUNSUPPORTED
             return False
         self._check(rc, "dsc_cuda_fft_segmented")
+        return True
+
+    def fft_columns_twiddled(self, plan, x_ptr, out_ptr, cols, forward, col_offset, tw_lo, tw_hi, shift, total,
+                             work_ptr=0, work_bytes=0, stream=0):
+        """Column transforms of a natural-order block [n][cols] with the outer four-step twiddle applied, k-major
+        output; False when the shape is not covered."""
+        rc = self.lib.dsc_cuda_fft_columns_twiddled(C.byref(plan), x_ptr, out_ptr, cols, int(forward), col_offset,
+                                                    tw_lo, tw_hi, shift, total, work_ptr, work_bytes, stream)
+        if rc == -4:         # DSC_CUDA_EUNSUPPORTED
+            return False
+        self._check(rc, "dsc_cuda_fft_columns_twiddled")
         return True
 
     def rfft(self, plan, x_ptr, out_ptr, outer, x_n, inner, work_ptr=0, work_bytes=0, stream=0):

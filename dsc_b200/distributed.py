@@ -59,7 +59,8 @@ class ShardedFFT:
         self.tw_hi = torch.empty(1 << (lg - self.shift), dtype=dtype, device=self.device)
         self.api.fill_twiddles(self.tw_lo.data_ptr(), self.tw_lo.numel(), 1, self.N, self.prec, self._stream())
         self.api.fill_twiddles(self.tw_hi.data_ptr(), self.tw_hi.numel(), 1 << self.shift, self.N, self.prec, self._stream())
-        wb = max(self.api.work_bytes(self.plan1, self.rows), self.api.work_bytes(self.plan2, self.cols), 256)
+        wb = max(self.api.work_bytes(self.plan1, self.rows), self.api.work_bytes(self.plan2, self.cols),
+                 self.api.work_bytes_axis(self.plan1, 1, self.rows), 256)
         self.work = torch.empty(wb, dtype=torch.uint8, device=self.device)
 
     def _stream(self) -> int:
@@ -78,6 +79,11 @@ class ShardedFFT:
         blk = m[:, self.rank * self.rows:(self.rank + 1) * self.rows]
         return blk.t().contiguous().to(self.device)
 
+    def scatter_input_natural(self, x_full: torch.Tensor) -> torch.Tensor:
+        """The rank's column block in NATURAL order, local[n1][n2_local] = x[n1*N2 + n2] (input of forward_natural)."""
+        m = x_full.reshape(self.N1, self.N2)
+        return m[:, self.rank * self.rows:(self.rank + 1) * self.rows].contiguous().to(self.device)
+
     def gather_output(self, local_out: torch.Tensor) -> torch.Tensor:
         """Natural-order X on every rank from the block-transposed shards (all_gather + transpose)."""
         if self.P > 1:
@@ -89,6 +95,20 @@ class ShardedFFT:
         return full.t().contiguous().reshape(-1)                 # index k1 + N1*k2
 
     # ---- the transform -------------------------------------------------------------------------------
+    def forward_natural(self, local_cols: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+        """local_cols: [N1, N2/P], the rank's column block of x in natural order.  Steps 1 and 2 are ONE launch
+        (dsc_cuda_fft_columns_twiddled: both passes of the length-N1 transform as column passes, the outer
+        twiddle applied on the way out, k1-major output); shapes it does not cover are transposed and go through
+        forward()."""
+        assert local_cols.shape == (self.N1, self.rows) and local_cols.dtype == self.dtype and local_cols.is_contiguous()
+        api, s = self.api, self._stream()
+        send = torch.empty(self.N1, self.rows, dtype=self.dtype, device=self.device)
+        if api.fft_columns_twiddled(self.plan1, local_cols.data_ptr(), send.data_ptr(), self.rows, not inverse,
+                                    self.rank * self.rows, self.tw_lo.data_ptr(), self.tw_hi.data_ptr(), self.shift,
+                                    self.N, self.work.data_ptr(), self.work.numel(), s):
+            return self._exchange_and_finish(send, not inverse)
+        return self.forward(local_cols.t().contiguous(), inverse)
+
     def forward(self, local_in: torch.Tensor, inverse: bool = False) -> torch.Tensor:
         """local_in: [N2/P, N1] (n2-major shard).  Returns [N1/P, N2]: X[k1 + N1 k2] for this rank's k1 block."""
         assert local_in.shape == (self.rows, self.N1) and local_in.dtype == self.dtype and local_in.is_contiguous()
@@ -101,6 +121,12 @@ class ShardedFFT:
         send = torch.empty(self.N1, self.rows, dtype=self.dtype, device=self.device)
         api.transpose_twiddle(a.data_ptr(), send.data_ptr(), self.rows, self.N1, self.rank * self.rows,
                               self.tw_lo.data_ptr(), self.tw_hi.data_ptr(), self.shift, fwd, self.code, s)
+        return self._exchange_and_finish(send, fwd)
+
+    def _exchange_and_finish(self, send: torch.Tensor, fwd: bool) -> torch.Tensor:
+        """send[k1][n2_local] (twiddled) -> all-to-all -> N1/P local transforms of length N2."""
+        api, s = self.api, self._stream()
+        inverse = not fwd
         if self.P > 1:
             recv = torch.empty_like(send)                        # [q][k1_local][n2_local]
             dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)

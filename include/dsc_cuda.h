@@ -105,6 +105,17 @@ int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, 
                            int64_t seg_len, int64_t seg_stride, int forward,
                            void *work, size_t work_bytes, void *stream);
 
+/* First local step of the multi-GPU four-step, in one launch: x is the rank's natural-order column block
+ * [n][cols] (element (i, c) = x_global[i * all_cols + col_offset + c]); out[k][c] = FFT over i of column c,
+ * times W_total^((col_offset + c) * k) -- the twiddled, k-major matrix whose row blocks are the all-to-all's
+ * send slabs.  tw_lo / tw_hi / shift: the split tables of W_total (dsc_cuda_fill_twiddles).  The inverse
+ * (conjugate twiddles) carries the plan's own 1/n like dsc_cuda_fft.  DSC_CUDA_EUNSUPPORTED when the plan has no column decomposition or cols is not a power of two at
+ * least one tile wide (the caller then uses dsc_cuda_fft + dsc_cuda_transpose_twiddle).
+ * work: dsc_cuda_work_bytes_axis(plan, 1, cols). */
+int dsc_cuda_fft_columns_twiddled(const dsc_cuda_plan *plan, const void *x, void *out, int64_t cols, int forward,
+                                  int64_t col_offset, const void *tw_lo, const void *tw_hi, int shift, int64_t total,
+                                  void *work, size_t work_bytes, void *stream);
+
 /* rfft: real (outer, x_n, inner) -> complex (outer, n + 1, inner), plan REAL of order n. */
 int dsc_cuda_rfft(const dsc_cuda_plan *plan, const void *x, void *out,
                   int64_t outer, int x_n, int64_t inner,

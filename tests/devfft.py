@@ -139,6 +139,28 @@ class DevFFT:
         ok = self.api.fft_segmented(plan, self.mem.ptr(dx), self.mem.ptr(dout), lines, seg_len, lines * seg_len, forward, wp, wb)
         return self.mem.download(dout) if ok else None
 
+    def fft_columns_twiddled(self, x, col_offset, total, forward=True):
+        """x: [n][cols] natural-order column block; returns out[k][c] = FFT over i of column c times
+        W_total^((col_offset + c) k) (conjugated when not forward), or None when the shape is not covered."""
+        x = np.ascontiguousarray(x)
+        n, cols = x.shape
+        prec = 0 if x.dtype == np.complex64 else 1
+        plan = self.plan(n, cuda_api.FFT_COMPLEX, prec)
+        lg = int(total).bit_length() - 1
+        shift = (lg + 1) // 2
+        lo = self.mem.empty((1 << shift,), x.dtype)
+        hi = self.mem.empty((1 << (lg - shift),), x.dtype)
+        self.api.fill_twiddles(self.mem.ptr(lo), 1 << shift, 1, total, prec)
+        self.api.fill_twiddles(self.mem.ptr(hi), 1 << (lg - shift), 1 << shift, total, prec)
+        dx = self.mem.upload(x)
+        dout = self.mem.empty((n, cols), x.dtype)
+        nbytes = self.api.work_bytes_axis(plan, 1, cols)
+        w = self.mem.alloc(nbytes) if nbytes else None
+        ok = self.api.fft_columns_twiddled(plan, self.mem.ptr(dx), self.mem.ptr(dout), cols, forward, col_offset,
+                                           self.mem.ptr(lo), self.mem.ptr(hi), shift, total,
+                                           self.mem.ptr(w) if nbytes else 0, nbytes)
+        return self.mem.download(dout) if ok else None
+
     def fft(self, x, n=-1, axis=-1):
         return self._cfft(x, n, axis, True)
 

@@ -30,6 +30,10 @@ def main():
     local = f.scatter_input(torch.from_numpy(x))
     out = f.forward(local)
     X = f.gather_output(out).cpu().numpy()
+    # the natural-order entry (steps 1 and 2 as one launch of column passes where the shape is covered)
+    out_nat = f.forward_natural(f.scatter_input_natural(torch.from_numpy(x)))
+    nat_err = float(torch.linalg.norm(out_nat - out) / torch.linalg.norm(out))
+    assert nat_err < 2e-6, nat_err
     back = f.gather_output(f.forward(f.scatter_input(torch.from_numpy(X)), inverse=True)).cpu().numpy()
     if rank == 0:
         from oracle import port

@@ -29,7 +29,7 @@ def test_sharded_four_step_gloo(world, lg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lg", [20, 24])
+@pytest.mark.parametrize("lg", [20, 24, 26])
 def test_sharded_four_step_nccl(lg):
     import torch
     world = min(torch.cuda.device_count(), 8)

@@ -9,7 +9,7 @@ from tests.devfft import DevFFT
 from tests.util import load_golden, randn, rel_l2, TOL
 # the emulated suite's cases run unchanged against the `dev` fixture defined below
 from tests.test_kernels_emulated import (  # noqa: F401
-    TIGHT, test_all_axes_pad_crop, test_c2c_last_axis, test_cmul, test_fused_filter, test_many_lines_partial_blocks,
+    TIGHT, test_columns_with_outer_twiddle, test_all_axes_pad_crop, test_c2c_last_axis, test_cmul, test_fused_filter, test_many_lines_partial_blocks,
     test_non_pow2_lengths, test_rfft_axes_and_length_rules, test_rfft_irfft_dense_whole_blocks, test_rfft_irfft_last_axis,
     test_two_pass_along_strided_axis, test_two_pass_c2c, test_two_pass_real, test_two_pass_segmented_rows)
 

@@ -202,6 +202,25 @@ def test_two_pass_along_strided_axis(dev, dtype, lg, outer, inner):
     assert rel_l2(dev.fft(xr, n=n, axis=1), port.fft(xr, n=n, axis=1)) < TIGHT[dtype]
 
 
+@pytest.mark.parametrize("dtype,lg,cols", [("complex64", 15, 64), ("complex64", 13, 128), ("complex128", 14, 32)])
+def test_columns_with_outer_twiddle(dev, dtype, lg, cols):
+    """First local step of the multi-GPU four-step in one launch: column transforms of a natural-order block,
+    times the outer twiddle, k-major."""
+    rng = np.random.default_rng(lg + cols)
+    n, all_cols, off = 1 << lg, 4 * cols, 2 * cols
+    x = randn(rng, (n, cols), dtype)
+    y = dev.fft_columns_twiddled(x, off, n * all_cols)
+    assert y is not None
+    k = np.arange(n, dtype=np.float64)[:, None]
+    c = (off + np.arange(cols, dtype=np.float64))[None, :]
+    want = port.fft(x, axis=0).astype(np.complex128) * np.exp(-2j * np.pi * ((k * c) % (n * all_cols)) / (n * all_cols))
+    assert rel_l2(y, want.astype(dtype)) < TIGHT[dtype] * 2
+    yi = dev.fft_columns_twiddled(x, off, n * all_cols, forward=False)
+    wanti = np.fft.ifft(x.astype(np.complex128), axis=0) * np.exp(2j * np.pi * ((k * c) % (n * all_cols)) / (n * all_cols))
+    assert rel_l2(yi, wanti.astype(dtype)) < TIGHT[dtype] * 2
+    assert dev.fft_columns_twiddled(x[:1024].copy(), off, 1024 * all_cols) is None      # no column decomposition
+
+
 def test_two_pass_chunked_work_buffer():
     d = DevFFT(os.path.join(EMUL_DIR, "libdsc_emul.so"), work_lines=2)
     rng = np.random.default_rng(3)

