@@ -87,6 +87,8 @@ struct FftArgs {
     int packed_out;       // same for the real output of MODE_C2R / MODE_FILTER
     int seg_shift;        // four-step first pass, dense rows: a row is made of segments of 2^seg_shift elements that lie
     long long seg_extra;  // seg_extra elements further apart than their length (0 / 0: one contiguous row)
+    int seg_self;         // segment index whose data lives in ANOTHER buffer (-1: none): the part of the multi-GPU
+    long long seg_self_delta;   // exchange that never left this GPU; element offset of that buffer from x
     int keep_out;         // four-step second pass: 1 = a later kernel re-reads the output soon (plain stores, the
                           // rows stay in L2); 0 = streaming stores
 };
@@ -707,7 +709,10 @@ DSC_DEV void pass_first_tile(const FftArgs &a, const long long tile, const int p
             // segmented rows (the receive buffer of the multi-GPU exchange, [peer][line][part]): a segment is a
             // whole number of this thread's steps long, so its index depends on c alone
 #pragma unroll
-            for (int c = 0; c < E; ++c) v[c] = ld_stream(src + c * STEP + ((c * STEP) >> a.seg_shift) * a.seg_extra);
+            for (int c = 0; c < E; ++c) {
+                const long long seg = (c * STEP) >> a.seg_shift;
+                v[c] = ld_stream(src + c * STEP + seg * a.seg_extra + (seg == a.seg_self ? a.seg_self_delta : 0));
+            }
         }
     } else {
         const long long sbase = row_in * a.gi.ostride + (long long)q * a.gi.lstride + (long long)j * a.gi.estride;

@@ -835,7 +835,7 @@ int dsc_cuda_fft_columns_twiddled(const dsc_cuda_plan *plan, const void *x, void
 }
 
 int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, int64_t lines,
-                           int64_t seg_len, int64_t seg_stride, int forward,
+                           int64_t seg_len, int64_t seg_stride, int self_seg, const void *self_x, int forward,
                            void *work, size_t work_bytes, void *stream) {
     if (!plan_ok(plan) || !x || !out || lines < 0 || seg_len < 1 || seg_stride < seg_len)
         return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_segmented: bad argument");
@@ -852,6 +852,14 @@ int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, 
     a.in_kind = IN_COMPLEX;
     a.seg_shift = seg_shift;
     a.seg_extra = (long long)(seg_stride - seg_len);
+    a.seg_self = -1;
+    if (self_seg >= 0 && self_x != nullptr) {
+        const size_t es = plan->dtype == DSC_CUDA_F32 ? sizeof(float2) : sizeof(double2);
+        const ptrdiff_t d = (const char *)self_x - (const char *)x;
+        if (d % (ptrdiff_t)es != 0) return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_segmented: self_x is not element-aligned with x");
+        a.seg_self = self_seg;
+        a.seg_self_delta = (long long)(d / (ptrdiff_t)es);
+    }
     if (plan->dtype == DSC_CUDA_F32)
         return forward ? four_step<float, true>(plan, a, lines, work, work_bytes, out, n, false, stream)
                        : four_step<float, false>(plan, a, lines, work, work_bytes, out, n, true, stream);

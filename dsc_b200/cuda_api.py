@@ -56,7 +56,7 @@ class CudaApi:
         L.dsc_cuda_fft.argtypes = [pp, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_fft_segmented.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
-                                             C.c_void_p, C.c_size_t, C.c_void_p]
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_fft_columns_twiddled.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p,
                                                     C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_rfft.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
@@ -100,11 +100,13 @@ class CudaApi:
         self._check(self.lib.dsc_cuda_fft(C.byref(plan), x_ptr, x_dtype, out_ptr, outer, x_n, inner,
                                           int(forward), work_ptr, work_bytes, stream), "dsc_cuda_fft")
 
-    def fft_segmented(self, plan, x_ptr, out_ptr, lines, seg_len, seg_stride, forward, work_ptr=0, work_bytes=0, stream=0):
-        """Lines stored as n/seg_len segments (segment s of line r at x + s*seg_stride + r*seg_len); returns False
-        when this plan / segment size is not covered (caller un-interleaves and uses fft)."""
-        rc = self.lib.dsc_cuda_fft_segmented(C.byref(plan), x_ptr, out_ptr, lines, seg_len, seg_stride, int(forward),
-                                             work_ptr, work_bytes, stream)
+    def fft_segmented(self, plan, x_ptr, out_ptr, lines, seg_len, seg_stride, forward, work_ptr=0, work_bytes=0, stream=0,
+                      self_seg=-1, self_ptr=0):
+        """Lines stored as n/seg_len segments (segment s of line r at x + s*seg_stride + r*seg_len; segment self_seg
+        read from self_ptr instead); returns False when this plan / segment size is not covered (caller
+        un-interleaves and uses fft)."""
+        rc = self.lib.dsc_cuda_fft_segmented(C.byref(plan), x_ptr, out_ptr, lines, seg_len, seg_stride, self_seg, self_ptr,
+                                             int(forward), work_ptr, work_bytes, stream)
         if rc == -4:         # DSC_CUDA_EUNSUPPORTED
             return False
         self._check(rc, "dsc_cuda_fft_segmented")

@@ -10,7 +10,8 @@ box).  Index split  n = n1*N2 + n2,  k = k1 + N1*k2:
   step 1     : N2/P local transforms of length N1          (dsc_cuda_fft, sm_100a kernels)
   step 2     : times W_N^{n2 k1} and transpose to [k1][n2_local] (dsc_cuda_transpose_twiddle): the slab
                for peer q, k1 in block q, is then contiguous
-  step 3     : all-to-all of the P slabs                    (the ONE exchange; NCCL)
+  step 3     : all-to-all of the slabs                      (the ONE exchange; NCCL.  The slab a rank would send to
+               itself stays in the send buffer and is read from there by step 4)
   step 4     : N1/P local transforms of length N2, read straight from the receive buffer [peer][k1_local][n2_local]
                (dsc_cuda_fft_segmented; short N2: un-interleave to [k1_local][n2] first)
   layout out : rank p owns k1 in block p: local[k1_local][k2] = X[k1 + N1*k2]   (block-transposed order)
@@ -129,13 +130,27 @@ class ShardedFFT:
         inverse = not fwd
         if self.P > 1:
             recv = torch.empty_like(send)                        # [q][k1_local][n2_local]
-            dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+            slab = self.cols * self.rows
+            in_place = self.plan2.lg_n2 != 0 and self.device.type == "cuda"
+            if in_place:
+                # the slab a rank would send to itself stays where it is: the exchange moves the P-1 others only,
+                # and the second transform reads that segment from the send buffer
+                flat_s, flat_r = send.view(-1), recv.view(-1)
+                empty = flat_s[:0]
+                ins = [empty if q == self.rank else flat_s[q * slab:(q + 1) * slab] for q in range(self.P)]
+                outs = [flat_r[:0] if q == self.rank else flat_r[q * slab:(q + 1) * slab] for q in range(self.P)]
+                dist.all_to_all(outs, ins, group=self.group)
+            else:
+                dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
             out = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
             # line k1_local is P segments of N2/P points, one per source rank: transformed where it lies when the
             # plan is a two-pass one (the first pass reads segmented rows), else un-interleaved first
-            if api.fft_segmented(self.plan2, recv.data_ptr(), out.data_ptr(), self.cols, self.rows,
-                                 self.cols * self.rows, fwd, self.work.data_ptr(), self.work.numel(), s):
+            if api.fft_segmented(self.plan2, recv.data_ptr(), out.data_ptr(), self.cols, self.rows, slab, fwd,
+                                 self.work.data_ptr(), self.work.numel(), s,
+                                 self.rank if in_place else -1, send.data_ptr() if in_place else 0):
                 return out
+            if in_place:
+                recv.view(self.P, slab)[self.rank].copy_(send.view(self.P, slab)[self.rank])
             b = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
             b.view(self.cols, self.P, self.rows).copy_(recv.view(self.P, self.cols, self.rows).permute(1, 0, 2))
         else:

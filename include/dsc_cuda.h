@@ -100,9 +100,11 @@ int dsc_cuda_fft(const dsc_cuda_plan *plan, const void *x, int x_dtype, void *ou
 /* fft / ifft of `lines` complex lines of plan->n points whose storage is SEGMENTED: line r consists of
  * n / seg_len segments of seg_len contiguous elements, segment s of line r at x + s*seg_stride + r*seg_len
  * -- the receive buffer [peer][line][part] of the multi-GPU four-step's all-to-all, transformed without
- * first un-interleaving it.  Two-pass plans only; seg_len a power of two >= n / 32 (float) or n / 16 (double). */
+ * first un-interleaving it.  self_seg >= 0: that segment is read from self_x instead (same layout and element
+ * alignment as x) -- the slab a rank "sends to itself" stays in the send buffer and never moves.
+ * Two-pass plans only; seg_len a power of two >= n / 32 (float) or n / 16 (double). */
 int dsc_cuda_fft_segmented(const dsc_cuda_plan *plan, const void *x, void *out, int64_t lines,
-                           int64_t seg_len, int64_t seg_stride, int forward,
+                           int64_t seg_len, int64_t seg_stride, int self_seg, const void *self_x, int forward,
                            void *work, size_t work_bytes, void *stream);
 
 /* First local step of the multi-GPU four-step, in one launch: x is the rank's natural-order column block

@@ -125,7 +125,7 @@ class DevFFT:
         self.api.fft(plan, self.mem.ptr(dx), _CODE[x.dtype], self.mem.ptr(dout), outer, x_n, inner, forward, wp, wb)
         return self.mem.download(dout)
 
-    def fft_segmented(self, segs, forward=True):
+    def fft_segmented(self, segs, forward=True, self_seg=-1):
         """segs: [S][lines][seg_len] complex (line r = concatenation of segs[:, r, :]).  Returns [lines][S*seg_len]
         or None when the library does not cover the shape."""
         segs = np.ascontiguousarray(segs)
@@ -136,7 +136,17 @@ class DevFFT:
         dx = self.mem.upload(segs)
         dout = self.mem.empty((lines, n), segs.dtype)
         w, wp, wb = self._work(plan, lines)
-        ok = self.api.fft_segmented(plan, self.mem.ptr(dx), self.mem.ptr(dout), lines, seg_len, lines * seg_len, forward, wp, wb)
+        self_ptr = 0
+        if self_seg >= 0:
+            # the self segment comes from a second buffer of the same layout; poison it in the first one
+            other = segs.copy()
+            segs = segs.copy()
+            segs[self_seg] = np.nan
+            dx = self.mem.upload(segs)
+            dself = self.mem.upload(other)
+            self_ptr = self.mem.ptr(dself)
+        ok = self.api.fft_segmented(plan, self.mem.ptr(dx), self.mem.ptr(dout), lines, seg_len, lines * seg_len, forward, wp, wb,
+                                    0, self_seg, self_ptr)
         return self.mem.download(dout) if ok else None
 
     def fft_columns_twiddled(self, x, col_offset, total, forward=True):

@@ -179,6 +179,8 @@ def test_two_pass_segmented_rows(dev, dtype, lg, segs):
     assert rel_l2(y, port.fft(x)) < TIGHT[dtype]
     z = dev.fft_segmented(np.ascontiguousarray(y.reshape(3, segs, n // segs).transpose(1, 0, 2)), forward=False)
     assert rel_l2(z, x) < TIGHT[dtype]
+    # one segment served from a second buffer (the slab a rank keeps instead of sending it to itself)
+    assert rel_l2(dev.fft_segmented(parts, self_seg=segs - 1), port.fft(x)) < TIGHT[dtype]
     assert dev.fft_segmented(parts[:, :, :64].copy()) is None      # single-pass length: not covered, caller copies
 
 
