@@ -622,12 +622,22 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
 // measured +1.2-1.7 % in same-box A/B runs (0.881 -> 0.892-0.896 of the copy peak); 6 blocks (42 registers)
 // spill and lose 15 %.  Shorter float
 // lines and all double lines spill a few registers under the same cap and gain nothing, so they keep 4 blocks.
-template <typename T> __host__ __device__ constexpr int lines_min_blocks(int mode, int lg_n) {
-    return (mode == MODE_FAST && sizeof(T) == 4 && lg_n == 12) ? 5 : 1;
+// The dense packed-real kernels would otherwise hoist every load of a thread's 16 / 32 bin pairs and twiddles in
+// front of the arithmetic (113-154 registers, one or two blocks per SM): they are capped at the register budget
+// of their complex counterparts (no spills).  Same-box A/B: irfft 2^14 float +26 %, 2^13 double +22 %, rfft
+// 2^11-2^12 float +5-6 %, 2^12 double +11 %, everything else within +-2 %.
+#ifndef DSC_REAL_FAST_BLOCKS
+#define DSC_REAL_FAST_BLOCKS 1
+#endif
+template <typename T> __host__ __device__ constexpr int lines_min_blocks(int mode, int lg_n, int threads = 256) {
+    if (mode == MODE_FAST && sizeof(T) == 4 && lg_n == 12) return 5;
+    if (DSC_REAL_FAST_BLOCKS && (mode == MODE_R2C_FAST || mode == MODE_C2R_FAST) && threads <= 256)
+        return lg_n <= (sizeof(T) == 4 ? 12 : 11) ? 4 : 2;
+    return 1;
 }
 
 template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
-__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)), lines_min_blocks<T>(MODE, LG_N))
+__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)), lines_min_blocks<T>(MODE, LG_N, LPB * (1 << (LG_N - LG_E))))
 fft_lines(const FftArgs a) {
     DSC_DYN_SMEM(smem_raw);
     fft_lines_body<T, LG_N, LG_E, LPB, FWD, MODE>(a, (long long)blockIdx.x, smem_raw);
