@@ -629,11 +629,16 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
 #ifndef DSC_REAL_FAST_BLOCKS
 #define DSC_REAL_FAST_BLOCKS 1
 #endif
+// The generic modes (predicated loads, runtime geometry) have the same habit -- 112-208 registers for the
+// contiguous complex shape -- and get the same budget: 4 blocks of <= 256 threads with the standard register tile,
+// 2 with the double-size one.
 template <typename T> __host__ __device__ constexpr int lines_min_blocks(int mode, int lg_n, int threads = 256) {
     if (mode == MODE_FAST && sizeof(T) == 4 && lg_n == 12) return 5;
-    if (DSC_REAL_FAST_BLOCKS && (mode == MODE_R2C_FAST || mode == MODE_C2R_FAST) && threads <= 256)
-        return lg_n <= (sizeof(T) == 4 ? 12 : 11) ? 4 : 2;
-    return 1;
+    if (!DSC_REAL_FAST_BLOCKS || threads > 256 || mode == MODE_FAST) return 1;
+    const bool dense_real = mode == MODE_R2C_FAST || mode == MODE_C2R_FAST;
+    // (the generic double kernels and the shortest lines would spill 36-124 bytes under the cap: left alone)
+    if (!dense_real && (sizeof(T) == 8 || lg_n < 9)) return 1;
+    return lg_n <= (sizeof(T) == 4 ? 12 : 11) ? 4 : 2;
 }
 
 template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
