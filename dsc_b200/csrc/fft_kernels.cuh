@@ -636,8 +636,10 @@ template <typename T> __host__ __device__ constexpr int lines_min_blocks(int mod
     if (mode == MODE_FAST && sizeof(T) == 4 && lg_n == 12) return 5;
     if (!DSC_REAL_FAST_BLOCKS || threads > 256 || mode == MODE_FAST) return 1;
     const bool dense_real = mode == MODE_R2C_FAST || mode == MODE_C2R_FAST;
-    // (the generic double kernels and the shortest lines would spill 36-124 bytes under the cap: left alone)
-    if (!dense_real && (sizeof(T) == 8 || lg_n < 9)) return 1;
+    // (the shortest lines and the generic double kernels would spill 36-124 bytes under the full cap: the former
+    // are left alone, the latter get 3 blocks = 85 registers, <= 8 bytes of spills, +7..27 % in same-box A/B)
+    if (!dense_real && lg_n < 9) return 1;
+    if (!dense_real && sizeof(T) == 8) return lg_n <= 11 ? 3 : 1;
     return lg_n <= (sizeof(T) == 4 ? 12 : 11) ? 4 : 2;
 }
 
