@@ -21,6 +21,18 @@ def dev():
     return DevFFT(cuda_api.LIBDSC, backend="torch")
 
 
+@pytest.mark.parametrize("dtype,lg,outer,inner", [("complex64", 16, 3, 256), ("complex64", 18, 1, 64),
+                                                   ("complex128", 15, 2, 128), ("complex64", 14, 4, 1024)])
+def test_long_columns_gpu(dev, dtype, lg, outer, inner):
+    """Larger shapes of tests/test_kernels_emulated.py::test_two_pass_along_strided_axis (several chunks per slab,
+    several slabs, ring reuse)."""
+    rng = np.random.default_rng(lg + inner)
+    x = randn(rng, (outer, 1 << lg, inner), dtype)
+    y = dev.fft(x, axis=1)
+    assert rel_l2(y, port.fft(x, axis=1)) < TIGHT[dtype]
+    assert rel_l2(dev.ifft(y, axis=1), x) < TIGHT[dtype]
+
+
 def test_two_pass_chunked_work_buffer_gpu():
     d = DevFFT(cuda_api.LIBDSC, backend="torch", work_lines=2)
     rng = np.random.default_rng(3)
