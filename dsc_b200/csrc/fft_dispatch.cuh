@@ -33,8 +33,7 @@ template <typename T> constexpr int lg_e_for(int lg_n) {
     // 16- and 32-point lines: four threads per line (direct coalesced accesses, one warp-synchronous exchange)
     // instead of one or two threads per line behind a staged copy -- measured 3.9 -> 5.7 and 2.5 -> 5.7 TB/s
     if (lg_n == 4 || (lg_n == 5 && sizeof(T) == 4)) return lg_n - 2;
-    // (64 points as 8 x 8 with eight threads per line measured 5.6 -> 6.9 TB/s in a timing-only run; not adopted
-    // until it has been through the GPU parity suite)
+    if (lg_n == 6 && sizeof(T) == 4) return 3;              // 64 points as 8 x 8 with eight threads per line: 5.6 -> 6.9 TB/s
     return lg_n < Tile<T>::LG_E ? lg_n : Tile<T>::LG_E;
 }
 
