@@ -193,15 +193,21 @@ static void dev_unlink(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     buf->dev_prev = buf->dev_next = nullptr;
 }
 
+// An asynchronous download (dsc_cuda_download_async) is in flight: wait for THAT copy and retire its event.  Every
+// path that frees, rewrites or re-targets the buffer goes through here first, so the DMA never lands in a host block
+// that has gone back to the allocator and no stale event is waited on later.  Returns true when there was one.
+static bool finish_download(dsc_tensor_buffer *buf) noexcept {
+    if (!(buf->flags & DSC_BUF_DOWNLOADING)) return false;
+    dscdev::event_wait(buf->downloaded);               // (this copy only: later downloads may still be in flight)
+    dscdev::event_release(buf->downloaded);
+    buf->downloaded = nullptr;
+    buf->flags &= ~(DSC_BUF_HOST_STALE | DSC_BUF_DOWNLOADING);
+    return true;
+}
+
 static void download_now(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     byte *host = (byte *) buf + BUFFER_HEADER;
-    if (buf->flags & DSC_BUF_DOWNLOADING) {            // started by dsc_cuda_download_async: just wait for it
-        dscdev::event_wait(buf->downloaded);           // (this copy only: later downloads may still be in flight)
-        dscdev::event_release(buf->downloaded);
-        buf->downloaded = nullptr;
-        buf->flags &= ~(DSC_BUF_HOST_STALE | DSC_BUF_DOWNLOADING);
-        return;
-    }
+    if (finish_download(buf)) return;                  // started by dsc_cuda_download_async: just wait for it
     dscdev::stream_sync(0);
     dscdev::copy_d2h(host, ctx->dev_base + ctx->dev_alloc.nodes[buf->dev_node].off, buf->nbytes, 2);
     dscdev::stream_sync(2);
@@ -210,7 +216,8 @@ static void download_now(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
 
 void dsc_dev_drop(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     if (buf->dev_node < 0) return;
-    if (buf->flags & DSC_BUF_HOST_STALE) download_now(ctx, buf);
+    if (finish_download(buf)) {}                            // the mirror is still being read by the download stream
+    else if (buf->flags & DSC_BUF_HOST_STALE) download_now(ctx, buf);
     else if (ctx->residency == 2) dscdev::stream_sync(0);   // a launch may still be reading the mirror
     ctx->dev_alloc.release(buf->dev_node);
     buf->dev_node = -1;
@@ -218,19 +225,23 @@ void dsc_dev_drop(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     dev_unlink(ctx, buf);
 }
 
+// A block of the device arena; when it is full, the mirrors of tensors that are not operands of the running op are
+// only caches (residency >= 1) and are given up first.  -1 when even that does not make room.
+static int dev_alloc_evicting(dsc_ctx *ctx, const usize bytes) noexcept {
+    int node = ctx->dev_alloc.alloc(bytes);
+    if (node >= 0) return node;
+    dscdev::sync_all();
+    for (dsc_tensor_buffer *b = ctx->dev_list; b != nullptr;) {
+        dsc_tensor_buffer *next = b->dev_next;
+        if (b->busy == 0) dsc_dev_drop(ctx, b);             // busy != 0 marks operands of the running op
+        b = next;
+    }
+    return ctx->dev_alloc.alloc(bytes);
+}
+
 void *dsc_dev_ptr(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     if (buf->dev_node < 0) {
-        int node = ctx->dev_alloc.alloc(buf->nbytes);
-        if (node < 0) {
-            // make room: mirrors of tensors that are not part of the running op are only caches
-            dscdev::sync_all();
-            for (dsc_tensor_buffer *b = ctx->dev_list; b != nullptr;) {
-                dsc_tensor_buffer *next = b->dev_next;
-                if (b->busy == 0) dsc_dev_drop(ctx, b);     // pad_ != 0 marks operands of the running op
-                b = next;
-            }
-            node = ctx->dev_alloc.alloc(buf->nbytes);
-        }
+        const int node = dev_alloc_evicting(ctx, buf->nbytes);
         if (node < 0)
             DSC_LOG_FATAL("device arena exhausted: %.1fMB requested, %.1fMB of %.1fMB in use (raise dsc_ctx_init sizes or DSC_DEVICE_MEM)",
                           DSC_B_TO_MB(buf->nbytes), DSC_B_TO_MB(ctx->dev_alloc.used), DSC_B_TO_MB(ctx->dev_alloc.capacity));
@@ -244,7 +255,10 @@ void *dsc_dev_ptr(dsc_ctx *ctx, dsc_tensor_buffer *buf) noexcept {
     return ctx->dev_base + ctx->dev_alloc.nodes[buf->dev_node].off;
 }
 
-void dsc_host_written(dsc_tensor_buffer *buf) noexcept { buf->flags &= ~(DSC_BUF_DEV_VALID | DSC_BUF_HOST_STALE); }
+void dsc_host_written(dsc_tensor_buffer *buf) noexcept {
+    finish_download(buf);       // an asynchronous download still in flight would land on top of what the host wrote
+    buf->flags &= ~(DSC_BUF_DEV_VALID | DSC_BUF_HOST_STALE);
+}
 
 void dsc_host_needed(dsc_ctx *ctx, const dsc_tensor *x) noexcept {
     if (x != nullptr && (x->buffer->flags & DSC_BUF_HOST_STALE)) download_now(ctx, x->buffer);
@@ -518,7 +532,7 @@ dsc_fft_plan *dsc_plan_fft(dsc_ctx *ctx, const int n, const dsc_fft_type fft_typ
         if (fft_type != COMPLEX) DSC_LOG_FATAL("real transforms of order %d are outside the supported range", fft_n);
         bytes = (((usize) 1 << ((lg + 1) / 2)) + ((usize) 1 << (lg - (lg + 1) / 2))) * es + 2 * DEV_GRANULE;
     }
-    const int node = ctx->dev_alloc.alloc(bytes);
+    const int node = dev_alloc_evicting(ctx, bytes);
     if (node < 0) DSC_LOG_FATAL("device arena exhausted while planning an FFT of length %d (%.1fMB of tables)", fft_n, DSC_B_TO_MB(bytes));
     byte *mem = ctx->dev_base + ctx->dev_alloc.nodes[node].off;
 
@@ -656,8 +670,14 @@ void launch_chunk(dsc_ctx *ctx, const xform_job &j, const byte *dx, byte *dout, 
 
 void upload_if_needed(dsc_ctx *ctx, const dsc_tensor *t) noexcept {
     dsc_tensor_buffer *b = t->buffer;
+    const bool had_mirror = b->dev_node >= 0;
     void *d = dsc_dev_ptr(ctx, b);
     if (ctx->residency >= 1 && (b->flags & DSC_BUF_DEV_VALID)) return;
+    if (had_mirror) {                                          // earlier launches may still read the old contents
+        dscdev::Event *readers_done = dscdev::event_record(0);
+        dscdev::stream_wait(1, readers_done);
+        dscdev::event_release(readers_done);
+    }
     dscdev::copy_h2d(d, (byte *) b + BUFFER_HEADER, b->nbytes, 1);
     dscdev::Event *e = dscdev::event_record(1);
     dscdev::stream_wait(0, e);
@@ -674,9 +694,18 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
     bx->busy = bo->busy = 1;                                   // operands of the running op: not evictable
     if (j.spectrum) j.spectrum->buffer->busy = 1;
 
+    finish_download(bo);                                       // `out=` reused while its last download is still in flight
     const bool x_on_device = ctx->residency >= 1 && bx->dev_node >= 0 && (bx->flags & DSC_BUF_DEV_VALID);
+    const bool x_mirror_reused = !x_on_device && bx->dev_node >= 0;
     const byte *dx = (const byte *) dsc_dev_ptr(ctx, bx);
     byte *dout = (byte *) dsc_dev_ptr(ctx, bo);
+    if (x_mirror_reused) {
+        // the upload below overwrites a mirror that an earlier launch on the compute stream may still be reading
+        // (residency >= 1 after dsc_cuda_touch_host / a host write): order the upload stream behind it
+        dscdev::Event *readers_done = dscdev::event_record(0);
+        dscdev::stream_wait(1, readers_done);
+        dscdev::event_release(readers_done);
+    }
     if (j.spectrum) upload_if_needed(ctx, j.spectrum);
 
     const usize in_row = (usize) j.x_n * (usize) j.inner * DSC_DTYPE_SIZE[j.x->dtype];
@@ -730,8 +759,8 @@ void run_job(dsc_ctx *ctx, const xform_job &j) noexcept {
             ta = (usize) j.inner * (usize) j.x_n * DSC_DTYPE_SIZE[j.x->dtype];
             tb = (usize) j.inner * (usize) j.out_n * DSC_DTYPE_SIZE[j.out->dtype];
         }
-        tmp_nodes[0] = ctx->dev_alloc.alloc(ta);
-        tmp_nodes[1] = ctx->dev_alloc.alloc(tb);
+        tmp_nodes[0] = dev_alloc_evicting(ctx, ta);
+        tmp_nodes[1] = dev_alloc_evicting(ctx, tb);
         if (tmp_nodes[0] < 0 || tmp_nodes[1] < 0)
             DSC_LOG_FATAL("device arena exhausted: this transform needs %.1fMB of temporaries", DSC_B_TO_MB(ta + tb));
         jj.tmp_a = ctx->dev_base + ctx->dev_alloc.nodes[tmp_nodes[0]].off;
@@ -837,21 +866,26 @@ dsc_tensor *make_out(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, const i
 void fft_trace_args(char *dst, const int cap, const char *type, const int n, const int axis,
                     const dsc_tensor *x, const dsc_tensor *out) noexcept {
     if (!dsc_trace_recording()) { dst[0] = '\0'; return; }
-    char tx[200];
+    // always a complete JSON object: a field that does not fit is left out, never cut (the dump is one JSON array)
+    char tx[200], to[200];
     dsc_trace_describe_tensor(tx, sizeof(tx), x);
-    int o = snprintf(dst, (size_t) cap, "{\"type\": \"%s\", \"order\": %d, \"axis\": %d, \"x\": %s", type, n, axis, tx);
-    if (out != nullptr && o < cap) {
-        dsc_trace_describe_tensor(tx, sizeof(tx), out);
-        o += snprintf(dst + o, (size_t) (cap - o), ", \"out\": %s", tx);
+    int o = snprintf(dst, (size_t) cap, "{\"type\": \"%s\", \"order\": %d, \"axis\": %d", type, n, axis);
+    if (o < 0 || o >= cap - 1) { dst[0] = '\0'; return; }
+    const int lx = (int) strlen(tx);
+    if (o + 7 + lx + 1 < cap) o += snprintf(dst + o, (size_t) (cap - o), ", \"x\": %s", tx);
+    if (out != nullptr) {
+        dsc_trace_describe_tensor(to, sizeof(to), out);
+        const int lo = (int) strlen(to);
+        if (o + 9 + lo + 1 < cap) o += snprintf(dst + o, (size_t) (cap - o), ", \"out\": %s", to);
     }
-    if (o < cap) snprintf(dst + o, (size_t) (cap - o), "}");
+    snprintf(dst + o, (size_t) (cap - o), "}");
 }
 
 // fft / ifft: shape and dtype rules of dsc_internal_fft (dsc.cpp:2009-2071)
 dsc_tensor *dsc_internal_fft(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, int n, const int axis,
                              const bool forward) noexcept {
     DSC_ASSERT(x != nullptr);
-    char args[232];
+    char args[512];
     fft_trace_args(args, sizeof(args), forward ? "FFT" : "IFFT", n, axis, x, out);
     dsc_span span("dsc_internal_fft", "op;fft", args);
     dsc_require_device(ctx, forward ? "dsc_fft" : "dsc_ifft");
@@ -886,7 +920,7 @@ dsc_tensor *dsc_internal_fft(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out,
 dsc_tensor *dsc_internal_rfft(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, const int n, const int axis,
                               const bool forward) noexcept {
     DSC_ASSERT(x != nullptr);
-    char args[232];
+    char args[512];
     fft_trace_args(args, sizeof(args), forward ? "RFFT" : "IRFFT", n, axis, x, out);
     dsc_span span("dsc_internal_rfft", "op;fft", args);
     dsc_require_device(ctx, forward ? "dsc_rfft" : "dsc_irfft");
@@ -944,7 +978,7 @@ dsc_tensor *dsc_fft_filter(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const
                            dsc_tensor *DSC_RESTRICT out, const int n, const int axis) noexcept {
     DSC_ASSERT(x != nullptr);
     DSC_ASSERT(B != nullptr);
-    char args[232];
+    char args[512];
     fft_trace_args(args, sizeof(args), "FILTER", n, axis, x, out);
     dsc_span span("dsc_fft_filter", "op;fft", args);
     dsc_require_device(ctx, "dsc_fft_filter");

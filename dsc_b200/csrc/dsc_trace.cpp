@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int NAME_MAX_ = 48, CAT_MAX_ = 16, ARGS_MAX_ = 232;
+constexpr int NAME_MAX_ = 48, CAT_MAX_ = 16, ARGS_MAX_ = 512;   // two 4-D tensor descriptions plus the op's own fields (about 400 bytes)
 
 struct record {
     char name[NAME_MAX_];

@@ -448,8 +448,10 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     s.rows = (int)rows;
     long long lag = (3LL * ce->grid + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
     if (lag < 1) lag = 1;
+    // at most half the ring -- with a ring of ONE work row that is lag 0 (second pass of row r ticketed before the
+    // first pass of row r + 1): raising it back to 1 would ticket A(r + 1) ahead of the B(r) it has to wait for,
+    // and a grid smaller than a row's tiles would then spin forever.  decode_ticket handles lag 0.
     if (ring > 0 && lag > ring / 2) lag = ring / 2;
-    if (lag < 1) lag = 1;
     if (lag > rows) lag = rows;
     s.lag = (int)lag;
 

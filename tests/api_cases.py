@@ -134,6 +134,15 @@ def check_memory_accounting(dsc):
     assert dsc.device_used_mem() == base_d
 
 
+def _host_write(dsc, t, values):
+    """What a raw-pointer user of the C ABI does: announce the write (dsc_cuda_touch_host waits for a download that
+    is still in flight and invalidates the device mirror), then store through tensor.data."""
+    import ctypes
+    values = np.ascontiguousarray(values, dtype=t.dtype)
+    dsc._load().dsc_cuda_touch_host(dsc._get_ctx(), t.c)
+    ctypes.memmove(t.c.contents.data, values.ctypes.data, values.nbytes)
+
+
 def check_residency_modes(dsc):
     rng = np.random.default_rng(16)
     x = randn(rng, (32, 512), "complex64")
@@ -171,6 +180,28 @@ def check_residency_modes(dsc):
             for xi, zi in zip(xs, pending):
                 assert rel_l2(zi.numpy(), xi) < 1e-6
             del pending
+            # a result whose asynchronous download is still in flight is (a) freed, (b) reused as out=, (c) rewritten
+            # by the host: each must retire the pending copy first (no DMA into freed memory, no stale event)
+            big = randn(rng, (64, 4096), "complex64")
+            tb = dsc.from_numpy(big)
+            z1 = dsc.ifft(dsc.fft(tb))
+            dsc.download_async(z1)
+            del z1                                                   # (a)
+            z2 = dsc.ifft(dsc.fft(tb))
+            dsc.download_async(z2)
+            other = randn(rng, (64, 4096), "complex64")
+            z2 = dsc.ifft(dsc.fft(other), out=z2)                    # (b)
+            assert rel_l2(z2.numpy(), other) < 1e-6
+            z3 = dsc.ifft(dsc.fft(tb))
+            dsc.download_async(z3)
+            _host_write(dsc, z3, np.ones((64, 4096), np.complex64))  # (c): retires the pending copy, then writes
+            assert np.all(dsc.fft(z3).numpy()[:, 0] == 4096.0)
+            # the input mirror is overwritten by the next upload while the previous launch may still read it
+            for rep in range(4):
+                _host_write(dsc, tb, other * (rep + 1))
+                zi = dsc.ifft(dsc.fft(tb))
+                assert rel_l2(zi.numpy(), other * (rep + 1)) < 1e-6
+            del tb, z2, z3, zi
     finally:
         dsc.set_residency(0)
 
@@ -243,6 +274,20 @@ def check_traces(dsc):
     assert gpu and all(e["ph"] == "X" and e["dur"] >= 0 and e["args"]["n"] in (64, 32) for e in gpu)
     assert any(e["cat"] == "gpu;copy" for e in events)
     del y, r
+    # two 4-D tensor descriptions in one args object must still dump as valid JSON
+    x4 = dsc.from_numpy(randn(rng, (100, 100, 16, 16), "complex64"))
+    o4 = dsc.ifft(x4)
+    dsc.traces_record(True)
+    o4 = dsc.ifft(x4, out=o4)
+    dsc.traces_record(False)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "traces4.json")
+        dsc.dump_traces(path)
+        events = json.load(open(path))
+    dsc.clear_traces()
+    b4 = next(e for e in events if e["name"] == "dsc_internal_fft" and e["ph"] == "B")
+    assert b4["args"]["x"]["shape"] == "[100, 100, 16, 16]" and b4["args"]["out"]["shape"] == "[100, 100, 16, 16]"
+    del x4, o4
 
 
 def check_composed_paths(dsc):

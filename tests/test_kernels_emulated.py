@@ -234,6 +234,24 @@ def test_two_pass_chunked_work_buffer():
     assert rel_l2(d1.irfft(X), xr) < 1e-6
 
 
+def test_columns_one_row_work_buffer():
+    """A work buffer that holds ONE row of the column launch with several rows to do (ring == 1): the second pass of a
+    row must be ticketed before the first pass of the next row, or the persistent grid spins forever
+    (fft_launch.cu, four_step_columns_launch: lag 0)."""
+    from dsc_b200 import cuda_api
+    d = DevFFT(os.path.join(EMUL_DIR, "libdsc_emul.so"))
+    rng = np.random.default_rng(31)
+    outer, n, inner = 2, 8192, 128
+    x = randn(rng, (outer, n, inner), "complex64")
+    plan = d.plan(n, cuda_api.FFT_COMPLEX, 0)
+    nbytes = d.api.work_bytes_axis(plan, 1, inner)           # sized for one outer slab only
+    assert 0 < nbytes < d.api.work_bytes_axis(plan, outer, inner)
+    w = d.mem.alloc(nbytes)
+    dx, dout = d.mem.upload(x), d.mem.empty(x.shape, x.dtype)
+    d.api.fft(plan, d.mem.ptr(dx), 2, d.mem.ptr(dout), outer, n, inner, True, d.mem.ptr(w), nbytes)
+    assert rel_l2(d.mem.download(dout), port.fft(x, axis=1)) < 1e-6
+
+
 @pytest.mark.parametrize("dtype,lg", [("float32", 15), ("float64", 14)])
 def test_two_pass_real(dev, dtype, lg):
     rng = np.random.default_rng(lg)
