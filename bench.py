@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (config.workload): BASELINE.json configs[1] -- batched complex64 FFT along the last
+Headline workload (config.workload): BASELINE.json configs[1] -- batched complex64 FFT along the last
 axis, 65536 x 4096 points, one step = forward + inverse over the whole batch.
 Metric: GFLOP/s counted as 5*N*log2(N) per transform (the reference's own convention,
 benchmarks/python/bench_fft.py:44), whole job over all N GPUs.  N > 1 (launched by
@@ -14,9 +14,16 @@ the barrier and the max-over-ranks of the timings.
   value         device-resident: inputs already in HBM, dsc_cuda_fft (device-level C ABI) on the
                 current stream, timed with CUDA events, max over ranks.
   roofline      per-launch duration of fft_lines<> measured with CUDA events inside the timed loop
-                against the algorithmic bytes (16 B per point: one read + one write).
-  e2e           the same step through the drop-in tensor C ABI (dsc_fft / dsc_ifft of libdsc.so)
-                with HOST buffers: uploads and downloads inside the timed region.
+                against the algorithmic bytes (16 B per point: one read + one write); `sustained`
+                is the same figure over a >= 2 s back-to-back loop (power-capped clocks).
+  configs       (N = 1) every other BASELINE config and the complex64 2^10..2^20 sweep, device-resident
+                through the device-level C ABI, each with algorithmic GB/s, fraction of the measured
+                copy peak and the relative L2 distance to the oracle on sampled rows.
+  sharded       (N >= 2) BASELINE configs[4]: ONE complex64 FFT of 2^30 points over the N ranks
+                (four-step, NCCL all-to-all), exchange timed by its own events, sampled-bin parity.
+  e2e           the headline step through the drop-in tensor C ABI (dsc_fft / dsc_ifft of libdsc.so)
+                with HOST buffers: uploads and downloads inside the timed region; next to it the
+                measured pinned-copy ceiling of this box at this N.
   cpu_baseline  the unmodified reference (oracle/_ref/libdsc_ref.so, else the C port) on the
                 box's host cores, bounded sample, N = 1 / rank 0 only.
 --impl reference prints the reference-arm line (CPU, all host cores) for the same metric/config.
@@ -41,6 +48,7 @@ FLOP_PER_TRANSFORM = 5.0 * N_POINTS * LG_N
 BYTES_PER_TRANSFORM = 16.0 * N_POINTS            # complex64: 8 B read + 8 B written per point
 METRIC = "batched FFT GFLOP/s (5N*log2N)"
 WORKLOAD = "complex64 fft+ifft, last axis, 65536 x 4096 (BASELINE configs[1])"
+ORACLE_MARCH = "x86-64-v3 (oracle/Makefile; BASELINE.md says -march=native, but the .so travels to another host)"
 
 
 def log(*a):
@@ -50,9 +58,7 @@ def log(*a):
 # --------------------------------------------------------------------------------------------
 # reference / CPU baseline (oracle side: the only place bench.py touches oracle/)
 
-def _cpu_worker(args):
-    """One process = one single-threaded reference context (the reference has no threading)."""
-    lines, reps, seed, use_ref = args
+def _cpu_step_fn(lines, seed, use_ref):
     import numpy as np
     rng = np.random.default_rng(seed)
     x = (rng.standard_normal((lines, N_POINTS)) + 1j * rng.standard_normal((lines, N_POINTS))).astype(np.complex64)
@@ -66,11 +72,18 @@ def _cpu_worker(args):
             tz = ref.lib.dsc_ifft(ref.ctx, ty, None, -1, -1)
             ref.free(tz)
             ref.free(ty)
-    else:
-        from oracle import port
+        return step, ref
+    from oracle import port
 
-        def step():
-            port.ifft(port.fft(x))
+    def step():
+        port.ifft(port.fft(x))
+    return step, None
+
+
+def _cpu_worker(args):
+    """One process = one single-threaded reference context (the reference has no threading)."""
+    lines, reps, seed, use_ref = args
+    step, _keep = _cpu_step_fn(lines, seed, use_ref)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -81,37 +94,65 @@ def _cpu_worker(args):
 
 def cpu_reference_run(steps, warmup, lines_per_core=1024):
     """Whole-host throughput of the reference CPU FFT: one process per core, each doing fwd+inv over
-    `lines_per_core` lines per step.  Returns (gflops, seconds_per_step, cores, kind, sample)."""
+    `lines_per_core` lines per step; plus the library's native mode (ONE core) measured in this process,
+    which also makes the parent load oracle/_ref/libdsc_ref.so itself.
+    Returns a dict (gflops, sec, cores, kind, sample, one_core_gflops)."""
     from oracle import ref_harness
     use_ref = ref_harness.available()
     if not use_ref:
         from oracle import port
         port.lib()      # build / load once in the parent so workers do not race on make
+    if use_ref:
+        # the parent maps the reference library itself (no context: the reference keeps its allocators in
+        # function-static singletons, one context per process, and the workers are forked from this one)
+        import ctypes
+        ctypes.CDLL(ref_harness.REF_SO, mode=os.RTLD_LOCAL)
     cores = len(os.sched_getaffinity(0))
     ctx = mp.get_context("fork")
+    # 1 core, the reference's native mode: BASELINE.md section 3 method (2 warm-ups, min of 5)
+    one_lines = 256
+    with ctx.Pool(1) as pool:
+        one = pool.map_async(_cpu_worker, [(one_lines, 7, 999, use_ref)]).get(timeout=600)[0][2:]
+        pool.close()
+        pool.join()
+    one_core = one_lines * 2 * FLOP_PER_TRANSFORM / min(one) / 1e9
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(lines_per_core, warmup + steps, 1000 + i, use_ref) for i in range(cores)])
+        res = pool.map_async(_cpu_worker, [(lines_per_core, warmup + steps, 1000 + i, use_ref) for i in range(cores)]).get(timeout=900)
+        pool.close()
+        pool.join()     # workers exit normally
     # a step ends when the slowest core is done
     per_step = [max(r[i] for r in res) for i in range(warmup, warmup + steps)]
     sec = statistics.mean(per_step)
     gflops = cores * lines_per_core * 2 * FLOP_PER_TRANSFORM / sec / 1e9
     kind = "reference" if use_ref else "port"
-    sample = f"{cores} processes x {lines_per_core} lines x 4096 points, fwd+inv, mean of {steps} steps after {warmup} warm-ups"
-    return gflops, sec, cores, kind, sample
+    sample = (f"{cores} processes x {lines_per_core} lines x 4096 points, fwd+inv, mean of {steps} steps after {warmup} warm-ups "
+              f"(whole workload: {BATCH} lines; per-transform throughput reported)")
+    return {"gflops": gflops, "sec": sec, "cores": cores, "kind": kind, "sample": sample, "one_core_gflops": one_core,
+            "lines_per_step": cores * lines_per_core}
+
+
+def common_config(world, batch_per_gpu):
+    """Keys both arms print, so that their `config` dicts are comparable."""
+    return {"workload": WORKLOAD, "n": N_POINTS, "batch_per_gpu": batch_per_gpu, "step": "fft then ifft, out of place",
+            "parallelism": f"batch-sharded x{world}, no data-path collective"}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    gflops, sec, cores, kind, sample = cpu_reference_run(args.steps, args.warmup)
+    r = cpu_reference_run(args.steps, args.warmup)
+    cfg = common_config(args.gpus, BATCH)
+    cfg.update({"sample_reduction": f"{r['lines_per_step']} of {BATCH} lines per step (bounded CPU sample, BASELINE.md section 3)",
+                "note": "reference CPU FFT, single-threaded library, one process per host core",
+                "oracle_march": ORACLE_MARCH})
     line = {
-        "impl": "reference", "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": r["gflops"], "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex64 (f32 arithmetic)", "data": "synthetic N(0,1), seeded",
-        "config": {"workload": WORKLOAD, "note": "reference CPU FFT, single-threaded library, one process per host core; "
-                                                 "each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": cfg,
+        "cpu_baseline": {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "one_core_value": r["one_core_gflops"], "march": ORACLE_MARCH},
+        "e2e": {"value": r["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -197,6 +238,270 @@ def ncu_traffic_per_launch():
     return None
 
 
+def rel_l2(a, b):
+    import numpy as np
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+class DevBench:
+    """Device-resident timings through the device-level C ABI with torch-owned memory."""
+
+    def __init__(self, api, dev, peak):
+        import torch
+        self.torch, self.api, self.dev, self.peak = torch, api, dev, peak
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.launches = 0
+
+    def plan(self, n, fft_type, prec):
+        from dsc_b200 import cuda_api  # noqa: F401
+        nb = self.api.plan_bytes(n, fft_type, prec)
+        mem = self.torch.empty(nb, dtype=self.torch.uint8, device=self.dev)
+        return self.api.plan_build(n, fft_type, prec, mem.data_ptr(), nb, self.stream), mem
+
+    def timed(self, fn, reps, warm=3):
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def sweep_point(self, lg, total_points=1 << 27, reps=10, sample_rows=64):
+        """complex64 fft + ifft of 2^lg-point lines, 1 GiB per tensor (>> L2, no flush needed)."""
+        import numpy as np
+        from dsc_b200 import cuda_api
+        from oracle import port
+        torch, api = self.torch, self.api
+        n = 1 << lg
+        rows = total_points // n
+        g = torch.Generator(device=self.dev).manual_seed(100 + lg)
+        x = torch.view_as_complex(torch.randn(rows, n, 2, generator=g, device=self.dev, dtype=torch.float32))
+        y, z = torch.empty_like(x), torch.empty_like(x)
+        plan, _mem = self.plan(n, cuda_api.FFT_COMPLEX, cuda_api.F32)
+        wb = api.work_bytes(plan, rows)
+        work = torch.empty(max(wb, 16), dtype=torch.uint8, device=self.dev)
+
+        def step():
+            api.fft(plan, x.data_ptr(), cuda_api.C32, y.data_ptr(), rows, n, 1, True, work.data_ptr(), wb, self.stream)
+            api.fft(plan, y.data_ptr(), cuda_api.C32, z.data_ptr(), rows, n, 1, False, work.data_ptr(), wb, self.stream)
+        ms = self.timed(step, reps)
+        self.launches += 2 * (reps + 3)
+        idx = torch.linspace(0, rows - 1, min(sample_rows, rows), device=self.dev).long()
+        xs = torch.view_as_real(x[idx]).cpu().numpy().view(np.complex64).reshape(len(idx), n)
+        ys = torch.view_as_real(y[idx]).cpu().numpy().view(np.complex64).reshape(len(idx), n)
+        zs = torch.view_as_real(z[idx]).cpu().numpy().view(np.complex64).reshape(len(idx), n)
+        err = rel_l2(ys, port.fft(xs))
+        gbs = 2 * 16.0 * rows * n / (ms * 1e-3) / 1e9
+        return {"lg_n": lg, "rows": rows, "ms_fwd_inv": ms, "gflops": 2 * rows * 5.0 * n * lg / (ms * 1e-3) / 1e9,
+                "algorithmic_gbs": gbs, "frac": gbs / self.peak, "rel_l2_vs_oracle": err, "roundtrip_rel_l2": rel_l2(zs, xs),
+                "sampled_rows": int(len(idx))}
+
+    def config3(self, rows=4096, n=262144, reps=3):
+        """BASELINE configs[2]: float64 rfft + irfft, rows x 262144, full size (8 GiB per tensor)."""
+        import numpy as np
+        from dsc_b200 import cuda_api
+        from oracle import port
+        torch, api = self.torch, self.api
+        order = n // 2
+        g = torch.Generator(device=self.dev).manual_seed(3)
+        x = torch.randn(rows, n, generator=g, device=self.dev, dtype=torch.float64)
+        X = torch.empty(rows, order + 1, dtype=torch.complex128, device=self.dev)
+        z = torch.empty_like(x)
+        plan, _mem = self.plan(order, cuda_api.FFT_REAL, cuda_api.F64)
+        wb = api.work_bytes(plan, rows)
+        work = torch.empty(max(wb, 16), dtype=torch.uint8, device=self.dev)
+
+        def fwd():
+            api.rfft(plan, x.data_ptr(), X.data_ptr(), rows, n, 1, work.data_ptr(), wb, self.stream)
+
+        def inv():
+            api.irfft(plan, X.data_ptr(), z.data_ptr(), rows, order + 1, 1, work.data_ptr(), wb, self.stream)
+        ms_f = self.timed(fwd, reps, warm=1)
+        ms_i = self.timed(inv, reps, warm=1)
+        ms = ms_f + ms_i
+        xs = x[:2].cpu().numpy()
+        err = rel_l2(X[:2].cpu().numpy(), port.rfft(xs))
+        err_rt = rel_l2(z[:2].cpu().numpy(), xs)
+        nbytes = 2.0 * rows * (8 * n + 16 * (order + 1))
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"config": 3, "workload": f"float64 rfft+irfft, {rows} x {n} (BASELINE configs[2], full size)", "ms": ms,
+                "ms_rfft": ms_f, "ms_irfft": ms_i, "gflops": 2 * rows * 2.5 * n * 18 / (ms * 1e-3) / 1e9,
+                "algorithmic_gbs": gbs, "frac": gbs / self.peak, "rel_l2_vs_oracle": err, "roundtrip_rel_l2": err_rt,
+                "tolerance": 1e-12, "sampled_rows": 2}
+
+    def config4(self, channels=2048, lg=20, reps=3):
+        """BASELINE configs[3]: fused filter irfft(rfft(s) * rfft(b)) on float32 channels of 2^20 samples; the
+        2048-channel slice one GPU holds."""
+        import numpy as np
+        from dsc_b200 import cuda_api
+        from oracle import port
+        torch, api = self.torch, self.api
+        n = 1 << lg
+        order = n // 2
+        g = torch.Generator(device=self.dev).manual_seed(4)
+        s = torch.randn(channels, n, generator=g, device=self.dev, dtype=torch.float32)
+        taps = np.zeros(n, np.float32)
+        taps[:128] = np.random.default_rng(5).standard_normal(128).astype(np.float32)
+        b = torch.from_numpy(taps).to(self.dev)
+        B = torch.empty(order + 1, dtype=torch.complex64, device=self.dev)
+        out = torch.empty_like(s)
+        plan, _mem = self.plan(order, cuda_api.FFT_REAL, cuda_api.F32)
+        wb = max(api.filter_work_bytes(plan, channels), api.work_bytes(plan, 1))
+        work = torch.empty(max(wb, 16), dtype=torch.uint8, device=self.dev)
+        api.rfft(plan, b.data_ptr(), B.data_ptr(), 1, n, 1, work.data_ptr(), wb, self.stream)
+
+        def step():
+            api.filter(plan, s.data_ptr(), B.data_ptr(), out.data_ptr(), channels, n, work.data_ptr(), wb, self.stream)
+        ms = self.timed(step, reps, warm=1)
+        err = rel_l2(out[:2].cpu().numpy(), np.stack([port.filter_fft(r, taps, n) for r in s[:2].cpu().numpy()]))
+        nbytes = 8.0 * channels * n
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"config": 4, "workload": f"fused filter rfft(s)*rfft(b)->irfft, float32, {channels} x 2^{lg} "
+                                         f"(BASELINE configs[3]: the 2048-channel slice of 16384 that one GPU holds)",
+                "ms": ms, "gflops": channels * 2 * 2.5 * n * lg / (ms * 1e-3) / 1e9, "algorithmic_gbs": gbs,
+                "frac": gbs / self.peak, "rel_l2_vs_oracle": err, "tolerance": 1e-5, "sampled_rows": 2}
+
+
+def config1_tensor_api(dsc):
+    """BASELINE configs[0]: README filterFFT through the tensor C ABI (device-resident operands)."""
+    import numpy as np
+    import torch
+    from oracle import port
+    s = np.random.default_rng(0).standard_normal(8192).astype(np.float32)
+    b = np.random.default_rng(1).standard_normal(128).astype(np.float32)
+    dsc.set_residency(2)
+    ts, tb = dsc.from_numpy(s), dsc.from_numpy(b)
+    B = dsc.rfft(tb, n=16384)
+    keep = {}
+
+    def three_calls():
+        keep["y"] = dsc.irfft(dsc.rfft(ts, n=16384) * B)
+
+    def fused():
+        keep["y"] = dsc.fft_filter(ts, B, n=16384)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+    t3 = timed(three_calls, 100)
+    want = port.filter_fft(s, b, 16384)
+    err3 = rel_l2(keep["y"].numpy(), want)
+    tf = timed(fused, 300)
+    errf = rel_l2(keep["y"].numpy(), want)
+    # the README slices the first len(s) + len(b) - 1 samples and compares with a direct convolution
+    conv = np.convolve(s.astype(np.float64), b.astype(np.float64))
+    err_conv = rel_l2(keep["y"].numpy()[:8319].astype(np.float64), conv)
+    keep.clear()
+    del ts, tb, B
+    dsc.set_residency(0)
+    return {"config": 1, "workload": "README filterFFT: rfft/irfft float32, signal 8192, 128 taps, fft_size 16384 (BASELINE configs[0])",
+            "us_per_call_fused": tf * 1e6, "us_per_call_three_calls": t3 * 1e6, "rel_l2_vs_oracle": errf,
+            "rel_l2_vs_oracle_three_calls": err3, "rel_l2_vs_f64_convolution": err_conv, "tolerance": 1e-5,
+            "api": "tensor C ABI (dsc_rfft, dsc_mul, dsc_irfft / dsc_fft_filter), operands device-resident, host-clock timed "
+                   "(latency-bound: one 64 KiB line)"}
+
+
+def copy_ceiling(dev, barrier, max_over_ranks, nbytes=1 << 30, reps=3):
+    """What this box's host<->device path can do at this N: one pinned cudaMemcpyAsync per direction, all ranks at
+    once -- H2D alone, D2H alone, and both directions together.  GB/s per rank."""
+    import torch
+    host_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(host_a, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    host_b.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0) / reps
+    run(True, True)
+    res = {"h2d_alone_gbs": nbytes / run(True, False) / 1e9, "d2h_alone_gbs": nbytes / run(False, True) / 1e9}
+    both = run(True, True)
+    res["duplex_gbs_each_way"] = nbytes / both / 1e9
+    res["how"] = "torch pinned 1 GiB buffers, one cudaMemcpyAsync per direction per rep, all ranks at once, per-rank GB/s"
+    return res
+
+
+def sharded_leg(api, dev, rank, world, barrier, max_over_ranks, lg=30, reps=3):
+    """BASELINE configs[4] at P = world: one complex64 FFT of 2^lg points, four-step, NCCL all-to-all."""
+    import torch
+    import torch.distributed as dist
+    from dsc_b200.distributed import ShardedFFT
+    n = 1 << lg
+    f = ShardedFFT(n, api=api, device=dev)
+    g = torch.Generator(device=dev).manual_seed(6 + rank)
+    local_cols = torch.view_as_complex(torch.randn(f.N1, f.rows, 2, generator=g, device=dev, dtype=torch.float32))
+    out = None
+    for _ in range(2):
+        out = f.forward_natural(local_cols)
+    barrier()
+    f.events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = f.forward_natural(local_cols)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+    ex = [a.elapsed_time(b) for a, b in f.events]
+    ex_ms = max_over_ranks(statistics.mean(ex)) if ex else 0.0
+    overlap = f.last_mode
+    f.events = None
+
+    # sampled bins against a float64 DFT accumulated over all ranks:
+    # local_cols[n1][j] = x[n1*N2 + rank*rows + j]; out[i][k2] = X[(rank*cols + i) + N1*k2]
+    ks = [(0, 0), (f.cols // 2, 3), (f.cols - 1, f.N2 - 1), (1, f.N2 // 2)]
+    probes = torch.tensor([i + f.N1 * k2 for i, k2 in ks], device=dev, dtype=torch.int64)      # rank 0's bins
+    acc = torch.zeros(len(ks), 2, device=dev, dtype=torch.float64)
+    n2 = rank * f.rows + torch.arange(f.rows, device=dev, dtype=torch.int64)
+    step_rows = max(1, (1 << 21) // f.rows)
+    for r0 in range(0, f.N1, step_rows):
+        r1 = min(r0 + step_rows, f.N1)
+        nn = torch.arange(r0, r1, device=dev, dtype=torch.int64)[:, None] * f.N2 + n2[None, :]
+        blk = local_cols[r0:r1].to(torch.complex128)
+        for pi, k in enumerate(probes.tolist()):
+            ph = ((nn * k) % n).to(torch.float64) * (-2.0 * torch.pi / n)
+            sacc = (blk * torch.complex(torch.cos(ph), torch.sin(ph))).sum()
+            acc[pi, 0] += sacc.real
+            acc[pi, 1] += sacc.imag
+    dist.all_reduce(acc)
+    err = None
+    if rank == 0:
+        got = torch.stack([out[i, k2] for i, k2 in ks]).to(torch.complex128)
+        want = torch.complex(acc[:, 0], acc[:, 1])
+        err = float(((got - want).abs() / want.abs()).max().item())
+    bytes_each_way = 8.0 * n / world * (world - 1) / world
+    return {"config": 5, "workload": f"single complex64 FFT, 2^{lg} points, four-step N1={f.N1} x N2={f.N2} over {world} GPUs "
+                                     f"(BASELINE configs[4])",
+            "n_gpus": world, "ms": ms, "gflops": 5.0 * n * lg / (ms * 1e-3) / 1e9,
+            "hbm_gbs_per_gpu_algorithmic": 16.0 * n / world / (ms * 1e-3) / 1e9,
+            "exchange_ms": ex_ms, "exchange_bytes_per_gpu_each_way": bytes_each_way,
+            "exchange_gbs_per_gpu_each_way": bytes_each_way / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else None,
+            "nvlink_peak_gbs_per_direction": 900.0, "nvlink_measured_peer_copy_gbs": 770.0,
+            "exchange_share_of_total": ex_ms / ms if ms > 0 else None, "exchange_mode": overlap,
+            "sampled_bin_max_rel_err_vs_f64_dft": err, "tolerance": 1e-5, "reps": reps}
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -206,9 +511,10 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process: the workers are forked
-        gfl, sec, cores, kind, sample = cpu_reference_run(steps=5, warmup=2, lines_per_core=2048)
-        cpu = {"value": gfl, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample}
-        log(f"bench: cpu baseline {gfl:.1f} GFLOP/s on {cores} cores ({kind})")
+        r = cpu_reference_run(steps=5, warmup=2, lines_per_core=2048)
+        cpu = {"value": r["gflops"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "one_core_value": r["one_core_gflops"], "march": ORACLE_MARCH}
+        log(f"bench: cpu baseline {r['gflops']:.1f} GFLOP/s on {r['cores']} cores, {r['one_core_gflops']:.2f} on one ({r['kind']})")
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -228,6 +534,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     api = cuda_api.CudaApi()      # raises if libdsc.so is missing: no fallback
+    peak, peak_src = measured_peak_gbs()
     rows = BATCH
     # ---- device-resident leg ----------------------------------------------------------------
     g = torch.Generator(device=dev).manual_seed(2 + rank)
@@ -265,18 +572,42 @@ def run_ours(args, rank, world, local_rank):
     ms_total = max_over_ranks(t0.elapsed_time(t1))
     ms_per_step = ms_total / args.steps
     value = world * rows * 2 * FLOP_PER_TRANSFORM / (ms_per_step * 1e-3) / 1e9
+    gpu_launches = 2 * args.steps
 
     fwd_ms = [e[0].elapsed_time(e[1]) for e in launch_events]
     inv_ms = [e[1].elapsed_time(e[2]) for e in launch_events]
     launch_ms = statistics.mean(fwd_ms + inv_ms)
     algo_bytes = rows * BYTES_PER_TRANSFORM
     achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
-    peak, peak_src = measured_peak_gbs()
 
-    # parity spot check inside the bench (device result vs the oracle on a few rows)
-    err = float(((z[:64] - x[:64]).norm() / x[:64].norm()).item())
+    # parity inside the bench: the device result against the oracle (DSC's CPU FFT restated) on sampled rows
+    sustained = None
+    err_oracle = None
+    err_rt = float(((z[:64] - x[:64]).norm() / x[:64].norm()).item())
+    if rank == 0:
+        from oracle import port
+        idx = torch.linspace(0, rows - 1, 64, device=dev).long()
+        xs = torch.view_as_real(x[idx]).cpu().numpy().view(np.complex64).reshape(64, N_POINTS)
+        ys = torch.view_as_real(y[idx]).cpu().numpy().view(np.complex64).reshape(64, N_POINTS)
+        err_oracle = rel_l2(ys, port.fft(xs))
 
-    # ---- end-to-end leg: drop-in tensor C ABI with host buffers -------------------------------
+    if not args.no_e2e:
+        # the same launches back to back for >= 2 s: what the kernel sustains under the power cap
+        sus_steps = max(args.steps, int(2200.0 / ms_per_step))
+        barrier()
+        with ClockSampler(local_rank) as sus_clocks:
+            t0.record()
+            for _ in range(sus_steps):
+                step()
+            t1.record()
+            barrier()
+        sus_ms = max_over_ranks(t0.elapsed_time(t1)) / sus_steps
+        gpu_launches += 2 * sus_steps
+        sus_gbs = 2 * algo_bytes / (sus_ms * 1e-3) / 1e9
+        sustained = {"seconds": sus_ms * sus_steps / 1e3, "steps": sus_steps, "ms_per_step": sus_ms, "achieved": sus_gbs,
+                     "frac": sus_gbs / peak, "value": world * rows * 2 * FLOP_PER_TRANSFORM / (sus_ms * 1e-3) / 1e9,
+                     "clocks": sus_clocks.summary()}
+
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -285,13 +616,57 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
-    del y, z
+
     x_host = torch.view_as_real(x[: rows]).cpu().numpy().view(np.complex64).reshape(rows, N_POINTS)
-    del x
+    del x, y, z
+    torch.cuda.empty_cache()
+
+    # ---- every other BASELINE config + the length sweep (one GPU) --------------------------------
+    configs = None
+    if world == 1 and not args.no_configs:
+        db = DevBench(api, dev, peak)
+        configs = []
+        sweep = []
+        for lg in range(10, 21):
+            pt = db.sweep_point(lg)
+            sweep.append(pt)
+            log(f"bench: sweep 2^{lg}: {pt['algorithmic_gbs']:.0f} GB/s ({pt['frac']:.2f}) relL2 {pt['rel_l2_vs_oracle']:.2e}")
+            torch.cuda.empty_cache()
+        configs.append({"config": 2, "workload": WORKLOAD, "ms": ms_per_step, "gflops": value, "algorithmic_gbs": achieved,
+                        "frac": achieved / peak, "rel_l2_vs_oracle": err_oracle, "roundtrip_rel_l2": err_rt, "tolerance": 1e-5,
+                        "sampled_rows": 64})
+        c3 = db.config3()
+        log(f"bench: config 3: {c3['ms']:.2f} ms {c3['algorithmic_gbs']:.0f} GB/s ({c3['frac']:.2f}) relL2 {c3['rel_l2_vs_oracle']:.2e}")
+        configs.append(c3)
+        torch.cuda.empty_cache()
+        c4 = db.config4()
+        log(f"bench: config 4: {c4['ms']:.2f} ms {c4['algorithmic_gbs']:.0f} GB/s ({c4['frac']:.2f}) relL2 {c4['rel_l2_vs_oracle']:.2e}")
+        configs.append(c4)
+        torch.cuda.empty_cache()
+        configs.append({"config": "sweep", "workload": "complex64 fft+ifft, last axis, 2^27 points per tensor (1 GiB), N = 2^10 .. 2^20",
+                        "tolerance": 1e-5, "target_frac": 0.70, "points": sweep,
+                        "min_frac": min(p["frac"] for p in sweep), "max_rel_l2_vs_oracle": max(p["rel_l2_vs_oracle"] for p in sweep)})
+        gpu_launches += db.launches
+
+    # ---- one transform sharded over the ranks (BASELINE configs[4]) -----------------------------
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        try:
+            sharded = sharded_leg(api, dev, rank, world, barrier, max_over_ranks)
+        except Exception as e:      # noqa: BLE001  (a failure here must not lose the headline line)
+            sharded = {"config": 5, "error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+
+    # ---- end-to-end leg: drop-in tensor C ABI with host buffers -------------------------------
+    ceiling = copy_ceiling(dev, barrier, max_over_ranks)
     torch.cuda.empty_cache()
     import dsc_b200 as dsc
     tensor_bytes = rows * N_POINTS * 8
     dsc.init(4 * tensor_bytes + (1 << 28), 1 << 26)
+    if configs is not None:
+        c1 = config1_tensor_api(dsc)
+        log(f"bench: config 1: fused {c1['us_per_call_fused']:.1f} us, three calls {c1['us_per_call_three_calls']:.1f} us")
+        configs.insert(0, c1)
     tx = dsc.from_numpy(x_host)
     e2e_steps = max(3, min(args.steps, 10))
 
@@ -343,35 +718,46 @@ def run_ours(args, rank, world, local_rank):
     dsc.shutdown()
     e2e_value = world * rows * 2 * FLOP_PER_TRANSFORM / e2e_sec / 1e9
     e2e_strict_value = world * rows * 2 * FLOP_PER_TRANSFORM / strict_sec / 1e9
+    gpu_launches += 2 * 2 * (e2e_steps + 2)
 
     if world > 1:
         dist.barrier()
 
     if rank == 0:
+        cfg = common_config(world, rows)
+        cfg.update({"l2": "2 GiB per tensor >> 126 MB L2, no flush needed", "roundtrip_rel_l2": err_rt,
+                    "rel_l2_vs_oracle": err_oracle, "e2e_roundtrip_rel_l2": e2e_err, "sample_reduction": "none (whole workload every step)"})
+        e2e_gbs = tensor_bytes / e2e_sec / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "complex64 (f32 arithmetic)", "data": "synthetic N(0,1), seeded, generated on device",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": rows, "n": N_POINTS, "step": "fft then ifft, out of place",
-                       "l2": "2 GiB per tensor >> 126 MB L2, no flush needed", "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "roundtrip_rel_l2": err, "e2e_roundtrip_rel_l2": e2e_err},
+            "config": cfg,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": tensor_bytes, "d2h_bytes_per_step": tensor_bytes,
                     "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps,
+                    "h2d_gbs": e2e_gbs, "d2h_gbs": e2e_gbs, "copy_peak_gbs": ceiling["duplex_gbs_each_way"],
+                    "frac_of_copy_peak": e2e_gbs / ceiling["duplex_gbs_each_way"], "copy_ceiling": ceiling,
                     "api": "dsc_fft + dsc_ifft (libdsc.so tensor C ABI), x in the pinned host arena and uploaded every step, "
                            "result z downloaded every step (started with dsc_cuda_download_async, awaited after the next step is issued: "
                            "full-duplex PCIe), intermediate y kept on the device (dsc_cuda_set_residency(2))",
                     "strict": {"value": e2e_strict_value, "ms_per_step": strict_sec * 1e3, "h2d_bytes_per_step": 2 * tensor_bytes,
                                "d2h_bytes_per_step": 2 * tensor_bytes, "roundtrip_rel_l2": strict_err,
-                               "api": "same calls with the library default (residency 0): every call uploads its input and "
-                                      "downloads its output, so y crosses PCIe twice"}},
-            "gpu_launches": 2 * args.steps,
+                               "h2d_gbs": 2 * tensor_bytes / strict_sec / 1e9,
+                               "api": "same calls with the library default (residency 0), i.e. what the reference's unchanged wrapper "
+                                      "gets: every call uploads its input and downloads its output, so y crosses PCIe twice"}},
+            "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "kernel": "fft_lines<float,12,4,1,{fwd,inv},MODE_FAST>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
                          "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_ms,
-                         "launch_ms_fwd": statistics.mean(fwd_ms), "launch_ms_inv": statistics.mean(inv_ms), "peak_source": peak_src},
+                         "launch_ms_fwd": statistics.mean(fwd_ms), "launch_ms_inv": statistics.mean(inv_ms), "peak_source": peak_src,
+                         "sustained": sustained},
             "cpu_baseline": cpu,
         }
+        if configs is not None:
+            line["configs"] = configs
+        if sharded is not None:
+            line["sharded"] = sharded
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -385,6 +771,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs and the sweep (N = 1)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 2^30 transform (N >= 2)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

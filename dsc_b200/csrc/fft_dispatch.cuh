@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <utility>
 #include "fft_kernels.cuh"
+#include "fft_tma.cuh"
 
 namespace dscfft {
 
@@ -142,6 +143,50 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
 #define DSC_FUSED_MAKE_false_float(A, B) make_fused<float, false, A, B>(),
 #define DSC_FUSED_MAKE_true_double(A, B) make_fused<double, true, A, B>(),
 #define DSC_FUSED_MAKE_false_double(A, B) make_fused<double, false, A, B>(),
+
+// ---- TMA-fed four-step launches (fft_tma.cuh) -----------------------------------------------------------------
+#if !defined(DSC_EMUL)
+struct TmaEntry {
+    void (*fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
+    int lg_n1, lg_n2, l_a, l_b, box_a, box_b, smem;
+    int grid;
+    bool configured;
+};
+
+template <typename T, bool FWD, int LG_N1, int LG_N2>
+TmaEntry make_tma() {
+    TmaEntry e;
+    e.fn = four_step_tma<T, LG_N1, LG_N2, FWD>;
+    e.lg_n1 = LG_N1; e.lg_n2 = LG_N2;
+    e.l_a = tma_lines<T>(LG_N1); e.l_b = tma_lines<T>(LG_N2);
+    e.box_a = tma_box_rows(LG_N1); e.box_b = tma_box_rows(LG_N2);
+    e.smem = (int)sizeof(TmaSmem<T>) + 1024;
+    e.grid = 0;
+    e.configured = false;
+    return e;
+}
+
+// float: every fused pair from 2^15 up; double (16-byte elements, 4096-point tiles): passes of at most 512 points
+#define DSC_TMA_PAIRS_float(X) X(8, 7) X(8, 8) X(9, 8) X(9, 9) X(10, 9) X(10, 10)
+#define DSC_TMA_PAIRS_double(X) X(7, 7) X(8, 7) X(8, 8) X(9, 8) X(9, 9)
+
+template <typename T, bool FWD> TmaEntry *tma_entry(int lg_n1, int lg_n2);
+template <> TmaEntry *tma_entry<float, true>(int, int);
+template <> TmaEntry *tma_entry<float, false>(int, int);
+template <> TmaEntry *tma_entry<double, true>(int, int);
+template <> TmaEntry *tma_entry<double, false>(int, int);
+
+#define DSC_DEFINE_TMA(T, FWD)                                                             \
+    template <> TmaEntry *tma_entry<T, FWD>(int lg_n1, int lg_n2) {                        \
+        static TmaEntry table[] = {DSC_TMA_PAIRS_##T(DSC_TMA_MAKE_##FWD##_##T)};           \
+        for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
+        return nullptr;                                                                    \
+    }
+#define DSC_TMA_MAKE_true_float(A, B) make_tma<float, true, A, B>(),
+#define DSC_TMA_MAKE_false_float(A, B) make_tma<float, false, A, B>(),
+#define DSC_TMA_MAKE_true_double(A, B) make_tma<double, true, A, B>(),
+#define DSC_TMA_MAKE_false_double(A, B) make_tma<double, false, A, B>(),
+#endif
 
 // ---- two-pass transforms along a non-last axis (four_step_columns) --------------------------------------------
 struct ColumnsEntry {

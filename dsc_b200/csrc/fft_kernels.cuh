@@ -98,7 +98,7 @@ template <int LG_N, int LG_E> struct Sched {
     static constexpr int E = 1 << LG_E;
     static constexpr int TT = N / E;
     static constexpr int STAGES = LG_E == 0 ? 1 : (LG_N + LG_E - 1) / LG_E;
-    static constexpr int lg_r(int s) { return (LG_N - s * LG_E) < LG_E ? (LG_N - s * LG_E) : LG_E; }
+    static __host__ __device__ constexpr int lg_r(int s) { return (LG_N - s * LG_E) < LG_E ? (LG_N - s * LG_E) : LG_E; }
     // Padded length of one line in shared memory.  In the strided thread mapping adjacent lanes are
     // adjacent LINES at the same position, and when fewer than a full bank phase of lines fit in a block
     // the next lanes are the next position: the line stride must map (line, position) pairs of one phase

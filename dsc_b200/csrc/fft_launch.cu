@@ -253,6 +253,124 @@ inline size_t in_elem_size(const FftArgs &a, size_t real_size) {
     return (a.in_kind == IN_REAL || a.in_kind == IN_PAIRS) ? real_size : 2 * real_size;
 }
 
+
+#if !defined(DSC_EMUL)
+// ---- TMA-fed four-step (fft_tma.cuh): tensor maps and the launch -------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so the library keeps
+// linking against libcudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// [rows][outer][inner] tensor of elem_bytes-sized elements (8 or 16), described in 8-byte units; box = box_outer x box_inner
+bool encode_3d(CUtensorMap *map, const void *base, size_t elem_bytes, unsigned long long inner, unsigned long long outer,
+               unsigned long long rows, unsigned long long outer_stride_elems, unsigned long long row_stride_elems,
+               unsigned box_inner, unsigned box_outer) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return false;
+    const unsigned es = (unsigned)(elem_bytes / 8);
+    const cuuint64_t dims[3] = {inner * es, outer, rows};
+    const cuuint64_t strides[2] = {outer_stride_elems * elem_bytes, row_stride_elems * elem_bytes};
+    const cuuint32_t box[3] = {box_inner * es, box_outer, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool tma_disabled() {
+    static const bool off = [] { const char *e = getenv("DSC_NO_TMA"); return e != nullptr && *e != '\0' && *e != '0'; }();
+    return off;
+}
+
+// Returns 1 when the shape is not covered (the caller continues with four_step_fused), 0 on success, < 0 on error.
+template <typename T, bool FWD>
+int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long rows, void *work, size_t work_bytes,
+                         void *dst, long long dst_row_stride, bool scale, void *stream, bool keep_out) {
+    using V = cx<T>;
+    const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
+    TmaEntry *te = tma_entry<T, FWD>(p->lg_n1, p->lg_n2);
+    if (te == nullptr || tma_disabled()) return 1;
+    // dense complex rows, read in full, 16-byte aligned rows on both sides
+    if (first.in_kind != IN_COMPLEX || first.in_limit < n || first.seg_shift != 0 || first.gi.lstride != 1 || first.gi.estride != n2 ||
+        first.ring_in != 0 || (uintptr_t)first.x % 16 != 0 || (uintptr_t)dst % 16 != 0 ||
+        ((size_t)first.gi.ostride * sizeof(V)) % 16 != 0 || ((size_t)dst_row_stride * sizeof(V)) % 16 != 0 ||
+        first.gi.ostride < n || dst_row_stride < n || rows >= 0x7fffffffLL)
+        return 1;
+    const size_t row_bytes = (size_t)n * sizeof(V);
+    const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
+    if (work == nullptr || work_bytes < sync_bytes + row_bytes || (uintptr_t)work % 256 != 0) return 1;
+    if (!te->configured) {
+        cudaError_t err = cudaFuncSetAttribute((const void *)te->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
+        int dev = 0, sms = 0;
+        if (err == cudaSuccess) err = cudaGetDevice(&dev);
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) { cudaGetLastError(); return 1; }
+        te->grid = sms;                       // one block (two butterfly groups + the producer warp) per SM
+        te->configured = true;
+    }
+    const long long tiles_a = n2 / te->l_a, tiles_b = n1 / te->l_b;
+    if (rows * (tiles_a + tiles_b) >= 0x7fffffffLL) return 1;
+    long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
+    const long long cap = (long long)(((size_t)64 << 20) / row_bytes) > 4 ? (long long)(((size_t)64 << 20) / row_bytes) : 4;
+    if (ring > cap) ring = cap;
+    if (ring >= rows) ring = 0;
+    FourStepSync s{};
+    s.ticket = (unsigned *)work;
+    s.a_done = s.ticket + 1;
+    s.b_done = s.a_done + rows;
+    s.tiles_a = (int)tiles_a;
+    s.tiles_b = (int)tiles_b;
+    s.ring = (int)ring;
+    s.rows = (int)rows;
+    {
+        // a tile is published about four tile times after its ticket was taken, while the whole GPU takes
+        // ~grid tickets per tile time: put a row's second pass that far behind its first pass
+        long long lag = (4LL * te->grid + tiles_b + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
+        if (lag < 1) lag = 1;
+        if (ring > 0 && lag > ring / 2) lag = ring / 2;
+        if (lag > rows) lag = rows;
+        s.lag = (int)lag;
+    }
+    V *mid = (V *)((char *)work + sync_bytes);
+    CUtensorMap map_x, map_w, map_out;
+    const unsigned long long wrows = (unsigned long long)(ring ? ring : rows);
+    if (!encode_3d(&map_x, first.x, sizeof(V), (unsigned long long)n2, (unsigned long long)n1, (unsigned long long)rows,
+                   (unsigned long long)n2, (unsigned long long)first.gi.ostride, (unsigned)te->l_a, (unsigned)te->box_a) ||
+        !encode_3d(&map_w, mid, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, wrows,
+                   (unsigned long long)n1, (unsigned long long)n, (unsigned)te->l_b, (unsigned)te->box_b) ||
+        !encode_3d(&map_out, dst, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, (unsigned long long)rows,
+                   (unsigned long long)n1, (unsigned long long)dst_row_stride, (unsigned)te->l_b, (unsigned)te->box_b))
+        return 1;
+    TmaArgs a{};
+    a.work = mid;
+    a.ring = ring;
+    for (int i = 0; i < DSC_CUDA_MAX_STAGES; ++i) { a.tw_a[i] = p->tw1[i]; a.tw_b[i] = p->tw2[i]; }
+    a.tw_lo = p->tw_lo; a.tw_hi = p->tw_hi;
+    a.four_shift = p->four_shift; a.four_mask = (1 << p->four_shift) - 1;
+    a.do_scale = scale; a.scale = 1.0 / (double)n;
+    a.keep_out = keep_out;
+    const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
+    if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
+    const long long tiles = rows * (tiles_a + tiles_b);
+    const unsigned blocks = (unsigned)(tiles < te->grid ? tiles : te->grid);
+    te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    return check_launch("four_step_tma");
+}
+#endif
+
 // The two passes of the four-step decomposition n = n1*n2 of `rows` lines:
 //   A: for every n2, length-n1 transform over stride-n2 data, times W_n^(n2 k1) -> work[row][k1][n2]
 //   B: for every k1, length-n2 transform of the contiguous run work[row][k1][:] -> dst[row][k1 + n1 k2]
@@ -273,6 +391,14 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         first.gi = LineGeom{first.gi.ostride / 2, 1, n2};
         first.in_limit = n;
     }
+
+#if !defined(DSC_EMUL)
+    {
+        // dense complex rows: the TMA-fed launch (bulk tensor copies into shared memory, fft_tma.cuh)
+        const int rc = four_step_tma_launch<T, FWD>(p, first, rows, work, work_bytes, dst, dst_row_stride, scale, stream, keep_out);
+        if (rc <= 0) return rc;
+    }
+#endif
 
     FftArgs a = first;
     a.inner = n2;

@@ -1,0 +1,446 @@
+// fft_tma.cuh -- the two passes of the four-step transform fed by the Tensor Memory Accelerator.
+//
+// Replaces, for dense complex rows of 2^15 .. 2^20 points (float; double up to 2^18), the register-direct
+// tiles of four_step_fused: there the payload of a tile sits in 64 registers per thread while it travels to
+// and from memory, the register file is full at 16 warps per SM, and nothing but those 16 warps can hide the
+// DRAM / L2 latency (ncu: no unit above 40 %, stalls spread over load-queue throttling and payload latency).
+// Here the payload travels by bulk tensor copies (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) between
+// memory and three 64 KiB shared-memory buffers, signalled through mbarriers; the butterfly warps only ever
+// touch shared memory and registers, and one producer warp keeps loads and stores in flight around them.
+//
+//   n = n1 * n2, row x[i1][q] (i1 < n1 stride n2), result X[k1 + n1 k2] = out[k2][k1]
+//
+//   pass A  tile = L_A adjacent columns q, all i1: box [n1][L_A] of x  -> length-n1 transforms over i1, times
+//           W_n^(q k1), TRANSPOSED on the way: the tile leaves as L_A contiguous lines W[q][k1] of the work row
+//           -- one linear 64 KiB bulk store;
+//   pass B  tile = L_B adjacent k1, all q: box [n2][L_B] of the work row W[q][k1] -> length-n2 transforms over
+//           q -> box [n2][L_B] of out (row pitch n1).
+//
+// Tile layout in shared memory is [position][line] with a line extent of at least 64 bytes, which is both
+// what a 2-D tensor box delivers and conflict-free for "adjacent lanes on adjacent lines"; the one exchange
+// that turns the block around (pass A, before its last stage: threads come back as consecutive positions of
+// ONE line so the final layout is [line][position]) uses an XOR swizzle of the line index by the low
+// position bits.  Eight-line tiles (1024-point float passes) swizzle the 64-byte half of each 128-byte bank
+// phase as well.
+//
+// Ticket order, work-row ring and the per-row completion counters are those of four_step_fused
+// (FourStepSync, decode_ticket); they are handled by the producer thread alone.
+//
+// Reference work replaced: /root/reference/dsc/include/dsc_fft.h:57-103 (dsc_fft_pass2), :168-175 (1/N).
+#pragma once
+
+#if !defined(DSC_EMUL)
+
+#include <cuda.h>
+
+#include "dsc_cuda.h"
+#include "fft_kernels.cuh"
+
+namespace dscfft {
+
+namespace tma {
+
+DSC_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+DSC_DEV void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DSC_DEV void mbar_arrive(void *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DSC_DEV void mbar_arrive_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DSC_DEV bool mbar_try_wait(void *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+DSC_DEV void mbar_wait(void *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+DSC_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (a following bulk store reads them)
+DSC_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy acquire of a flag -> async-proxy (TMA) reads of the data it guards
+DSC_DEV void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+DSC_DEV unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+DSC_DEV unsigned long long policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// box (c0.., c1.., c2) of a 3-D tensor -> shared memory, completion on an mbarrier
+DSC_DEV void load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, void *bar, unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+DSC_DEV void store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src, unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+        ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(pol) : "memory");
+}
+DSC_DEV void store_linear(void *gdst, const void *src, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
+}
+DSC_DEV void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DSC_DEV void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DSC_DEV void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+}  // namespace tma
+
+// ---- geometry of one launch -------------------------------------------------------------------------------
+constexpr int TMA_TILE_BYTES = 64 * 1024;
+constexpr int TMA_BUFFERS = 3;
+constexpr int TMA_GROUPS = 2;                 // consumer groups of TMA_GROUP_THREADS threads
+constexpr int TMA_GROUP_THREADS = 256;
+constexpr int TMA_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 32;     // + the producer warp
+
+template <typename T> __host__ __device__ constexpr int tma_lg_e() { return sizeof(T) == 4 ? 5 : 4; }     // 32 / 16 points per thread
+template <typename T> __host__ __device__ constexpr int tma_tile_points() { return TMA_TILE_BYTES / (int)sizeof(cx<T>); }
+// lines per tile of a pass of 2^lg points
+template <typename T> __host__ __device__ constexpr int tma_lines(int lg) { return tma_tile_points<T>() >> lg; }
+// rows per tensor box (box extents are at most 256)
+__host__ __device__ constexpr int tma_box_rows(int lg) { return (1 << lg) < 256 ? (1 << lg) : 256; }
+
+struct TmaArgs {
+    void *work;                    // ring of work rows W[ring row][q][k1]
+    long long ring;                // 0 = one work row per row
+    const void *tw_a[DSC_CUDA_MAX_STAGES];     // stage tables of the length-n1 transform
+    const void *tw_b[DSC_CUDA_MAX_STAGES];     // stage tables of the length-n2 transform
+    const void *tw_lo, *tw_hi;     // W_n^p split tables
+    int four_shift, four_mask;
+    double scale;                  // applied by pass B when do_scale (1/n of the inverse)
+    int do_scale;
+    int keep_out;                  // the output is re-read soon by another kernel: keep it in L2
+};
+
+struct TmaTileDesc { unsigned role_a, row, r, exit; };
+
+template <typename T> struct TmaSmem {
+    using V = cx<T>;
+    static constexpr int TABLE_MAX = sizeof(T) == 4 ? 32 * 32 : 32 * 16;     // (c, line) inter-pass twiddles of one pass-A tile, per group
+    alignas(1024) unsigned char buf[TMA_BUFFERS][TMA_TILE_BYTES];
+    V table[TMA_GROUPS][TABLE_MAX];
+    unsigned long long full[TMA_BUFFERS];          // bytes of the tile have landed (producer + TMA -> consumers)
+    unsigned long long ready[TMA_BUFFERS];         // the finished tile lies in the buffer (consumers -> producer)
+    TmaTileDesc desc[TMA_BUFFERS];
+};
+
+// W_n^p from the two sqrt(n)-sized tables
+template <typename T> DSC_DEV cx<T> tma_twiddle(const TmaArgs &a, const unsigned p) {
+    const cx<T> lo = __ldg((const cx<T> *)a.tw_lo + (p & (unsigned)a.four_mask));
+    const cx<T> hi = __ldg((const cx<T> *)a.tw_hi + (p >> a.four_shift));
+    return cmul(lo, hi);
+}
+
+// ---- one tile on one consumer group -----------------------------------------------------------------------
+template <typename T, int LG_N, int L, bool FWD, bool TRANSPOSE>
+struct TmaTile {
+    using V = cx<T>;
+    static constexpr int LG_E = tma_lg_e<T>() < LG_N ? tma_lg_e<T>() : LG_N;
+    using Sc = Sched<LG_N, LG_E>;
+    static constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, STAGES = Sc::STAGES;
+    static constexpr int SLOTS = 128 / (int)sizeof(V);           // elements of one 128-byte bank phase: 16 / 8
+    static constexpr bool NARROW = L < SLOTS;                    // a phase spans two positions
+    static_assert(L * TT == TMA_GROUP_THREADS, "a tile is one register tile per thread of the group");
+    static_assert(L * 2 >= SLOTS, "lines of at least 64 bytes");
+    static_assert(!NARROW || (STAGES == 2 && LG_N == 2 * LG_E), "narrow tiles: two full-radix stages only");
+    static constexpr int LG_TT = LG_N - LG_E;
+    static constexpr int LG_SLOTS = SLOTS == 16 ? 4 : 3;
+    static constexpr int SW_BITS = LG_TT < LG_SLOTS ? LG_TT : LG_SLOTS;
+
+    // element index of (position, line) in the exchange layout.  JFAST: the readers are consecutive positions of one
+    // line (and, when a line has fewer threads than a phase has lanes, a few adjacent lines): the low position bits
+    // are XOR-ed into the high bits of the line's slot.
+    template <bool JFAST> static DSC_DEV int phys(const int pos, const int l) {
+        if constexpr (NARROW) {
+            // 8 lines of 8 bytes (4 of 16): the two positions of a phase are (j, j+1) for readers and (32 j + p,
+            // 32 (j+1) + p) for the first scatter -- flip the half by position bit LG_E so both differ in it, and
+            // rotate the line by the next position bits for the consecutive-position readers
+            const int row = (pos & ~1) | ((pos ^ (pos >> LG_E)) & 1);
+            return row * L + (l ^ ((pos >> 1) & (L - 1)));
+        } else if constexpr (JFAST) {
+            return pos * L + (l ^ ((pos & ((1 << SW_BITS) - 1)) << (LG_SLOTS - SW_BITS)));
+        } else {
+            return pos * L + l;
+        }
+    }
+
+    template <int S>
+    static DSC_DEV void stage(V (&v)[E], V *buf, const int l, const int j, const int l_last, const int j_last,
+                              const void *const *tw_all, const int bar_id) {
+        constexpr int LG_R = Sc::lg_r(S), R = 1 << LG_R, NB = E / R;
+        constexpr int LG_NS = S * LG_E, NS = 1 << LG_NS;
+        constexpr bool LAST = S == STAGES - 1;
+        constexpr bool NEXT_JFAST = TRANSPOSE && (S + 1 == STAGES - 1);
+        const V *__restrict__ tw = (const V *)tw_all[S];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int jj = j + b * TT;
+            const int k = jj & (NS - 1);
+            V r[R];
+#pragma unroll
+            for (int m = 0; m < R; ++m) r[m] = v[b + m * NB];
+            if constexpr (S > 0) {
+                if constexpr (R >= 8) {
+                    V w[R];
+#pragma unroll
+                    for (int m = 1; m < R; ++m) {
+                        if ((m & (m - 1)) == 0) w[m] = __ldg(tw + (m - 1) * NS + k);
+                        else {
+                            int hi = 1;
+                            while (hi * 2 <= m) hi *= 2;
+                            w[m] = cmul(w[hi], w[m - hi]);
+                        }
+                        r[m] = cmul_tw<FWD>(r[m], w[m]);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 1; m < R; ++m) r[m] = cmul_tw<FWD>(r[m], __ldg(tw + (m - 1) * NS + k));
+                }
+            }
+            Dft<R, FWD, T>::run(r);
+            if constexpr (LAST) {
+#pragma unroll
+                for (int p = 0; p < R; ++p) v[b + p * NB] = r[p];
+            } else {
+                if (b == 0) dsc_named_barrier(bar_id, TMA_GROUP_THREADS);    // every thread has read the previous layout
+                const int base = ((jj - k) << LG_R) + k;
+#pragma unroll
+                for (int p = 0; p < R; ++p) buf[phys<NEXT_JFAST>(base + p * NS, l)] = r[p];
+            }
+        }
+        if constexpr (!LAST) {
+            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+            const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
+            stage<S + 1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id);
+        }
+    }
+
+    // buf: the tile as the box delivered it, [position][line]; on return the finished tile, [line][position]
+    // (TRANSPOSE, times the inter-pass twiddle W_n^(q k1)) or [position][line] (times the inverse's 1/n).
+    static DSC_DEV void run(V *buf, V *table, const TmaArgs &a, const void *const *tw_all, const unsigned q0,
+                            const int gtid, const int bar_id) {
+        const int l = gtid % L, j = gtid / L;
+        const int l_last = TRANSPOSE ? gtid / TT : l, j_last = TRANSPOSE ? gtid % TT : j;
+        V v[E];
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = buf[(j + c * TT) * L + l];
+        V w0 = mk<T>((T)1, (T)0);
+        if constexpr (TRANSPOSE) {
+            // k1 = j + c TT: W^(q j) per thread, W^(q TT c) from a (c, line) table of the tile.  The previous tile's
+            // readers of the table are past this tile's first barrier only after they finished with it, so the table
+            // is rebuilt AFTER that barrier: between the scatter and the exchange barrier of the first stage.
+            w0 = tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
+        }
+        stage_first(v, buf, table, a, l, j, l_last, j_last, tw_all, q0, gtid, bar_id);
+        // every thread has read its last-stage inputs: the buffer may take the finished tile
+        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+        if constexpr (TRANSPOSE) {
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const V w = c == 0 ? w0 : cmul(w0, table[c * L + l_last]);
+                buf[l_last * N + j_last + c * TT] = cmul_tw<FWD>(v[c], w);
+            }
+        } else {
+            if (a.do_scale) {
+                const T s = (T)a.scale;
+#pragma unroll
+                for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
+            }
+#pragma unroll
+            for (int c = 0; c < E; ++c) buf[(j + c * TT) * L + l] = v[c];
+        }
+    }
+
+    // stage 0 with the table build folded in after its first barrier
+    static DSC_DEV void stage_first(V (&v)[E], V *buf, V *table, const TmaArgs &a, const int l, const int j,
+                                    const int l_last, const int j_last, const void *const *tw_all, const unsigned q0,
+                                    const int gtid, const int bar_id) {
+        static_assert(STAGES >= 2, "a pass has at least one exchange");
+        constexpr int R = 1 << Sc::lg_r(0), NB = E / R;
+        static_assert(NB == 1, "the first stage is a full-radix butterfly");
+        constexpr bool NEXT_JFAST = TRANSPOSE && (1 == STAGES - 1);
+        Dft<R, FWD, T>::run(v);
+        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // every thread of the group has read the delivered tile
+        const int base = j << Sc::lg_r(0);
+#pragma unroll
+        for (int p = 0; p < R; ++p) buf[phys<NEXT_JFAST>(base + p, l)] = v[p];
+        if constexpr (TRANSPOSE) {
+            for (int i = gtid; i < L * E; i += TMA_GROUP_THREADS) {
+                const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
+                table[i] = tma_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
+            }
+        }
+        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+        const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
+#pragma unroll
+        for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
+        stage<1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id);
+    }
+};
+
+// ---- the persistent launch --------------------------------------------------------------------------------
+// One block per SM: warps 0..15 are two consumer groups, warp 16 lane 0 is the producer.  The producer walks
+// the block's tile sequence t = 0, 1, 2, ...: tile t is transformed by group t % 2 in buffer t % 3.
+//   producer, tile t :  take a ticket -> store tile t-3 out of buffer t % 3 (when its group has finished it) and
+//                       wait until the copy has READ the buffer -> wait for the tile's dependency (all first-pass
+//                       tiles of the row; the second pass of the row that used the work row before) -> issue the
+//                       box loads -> wait for the stores issued so far to COMPLETE and publish their rows' counters.
+//   consumer, tile t :  wait full[t % 3] -> transform in place -> fence.proxy.async -> arrive on ready[t % 3].
+template <typename T, int LG_N1, int LG_N2, bool FWD>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const __grid_constant__ CUtensorMap map_out, const TmaArgs a, const FourStepSync s) {
+    using V = cx<T>;
+    constexpr int L_A = tma_lines<T>(LG_N1), L_B = tma_lines<T>(LG_N2);
+    constexpr int BOX_A = tma_box_rows(LG_N1), BOX_B = tma_box_rows(LG_N2);
+    using TileA = TmaTile<T, LG_N1, L_A, FWD, true>;
+    using TileB = TmaTile<T, LG_N2, L_B, FWD, false>;
+    static_assert(L_A * TileA::E <= TmaSmem<T>::TABLE_MAX, "inter-pass table");
+    DSC_DYN_SMEM(smem_raw);
+    // the tile buffers want 1024-byte alignment (box destinations): round the dynamic window up
+    TmaSmem<T> &sm = *reinterpret_cast<TmaSmem<T> *>(smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u));
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int b = 0; b < TMA_BUFFERS; ++b) {
+            tma::mbar_init(&sm.full[b], 1);
+            tma::mbar_init(&sm.ready[b], TMA_GROUP_THREADS);
+        }
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+
+    const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
+    if (tid >= TMA_GROUPS * TMA_GROUP_THREADS) {
+        // ------------------------------------------------------------------ producer
+        if (tid != TMA_GROUPS * TMA_GROUP_THREADS) return;
+        const unsigned long long pol_stream = tma::policy_evict_first(), pol_keep = tma::policy_evict_last();
+        constexpr unsigned HIST = TMA_BUFFERS + 1;  // tiles in the buffers + the one stored but not yet published
+        TmaTileDesc hist[HIST] = {};
+        unsigned next_store = 0, signaled = 0;      // tile sequence numbers
+
+        auto do_store = [&](const unsigned st) {
+            const int b = (int)(st % TMA_BUFFERS);
+            tma::mbar_wait(&sm.ready[b], (st / TMA_BUFFERS) & 1);
+            const TmaTileDesc d = hist[st % HIST];
+            if (d.role_a) {
+                // L_A contiguous lines W[q0 + l][k1] of the work row
+                const long long wrow = a.ring ? d.row % a.ring : d.row;
+                V *dst = (V *)a.work + ((wrow << LG_N2) + (long long)d.r * L_A << LG_N1);
+                tma::store_linear(dst, sm.buf[b], TMA_TILE_BYTES, pol_keep);
+            } else {
+                constexpr int ROWS = 1 << LG_N2;
+                constexpr int ES = sizeof(T) == 4 ? 1 : 2;          // double2 boxes are described in 8-byte elements
+#pragma unroll
+                for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
+                    tma::store_3d(&map_out, (int)d.r * L_B * ES, r0, (int)d.row, sm.buf[b] + (size_t)r0 * L_B * sizeof(V),
+                                  a.keep_out ? pol_keep : pol_stream);
+            }
+            tma::store_commit();
+            tma::store_wait_read();
+        };
+        auto signal_done = [&]() {
+            if (signaled == next_store) return;
+            tma::store_wait_all();
+            tma::fence_async_all();                 // async-proxy writes before the generic-proxy release below
+            for (; signaled < next_store; ++signaled) {
+                const TmaTileDesc d = hist[signaled % HIST];
+                dsc_signal_release((d.role_a ? s.a_done : s.b_done) + d.row);
+            }
+        };
+
+        unsigned pending = atomicAdd(s.ticket, 1u);
+        unsigned t = 0;
+        for (;; ++t) {
+            const unsigned ticket = pending;
+            if (ticket >= total) break;
+            pending = atomicAdd(s.ticket, 1u);
+            unsigned row, r;
+            bool role_a;
+            decode_ticket(s, ticket, role_a, row, r);
+            // the buffer: tile t - 3 has to leave first (its counters are published after this tile's loads are issued)
+            while (next_store + TMA_BUFFERS <= t) do_store(next_store++);
+            // the dependency; while it is open, finish the block's own earlier tiles (it may be one of them)
+            const unsigned *flag = nullptr;
+            unsigned target = 0;
+            if (!role_a) { flag = s.a_done + row; target = (unsigned)s.tiles_a; }
+            else if (s.ring && row >= (unsigned)s.ring) { flag = s.b_done + (row - s.ring); target = (unsigned)s.tiles_b; }
+            if (flag != nullptr) {
+                while (ld_acquire(flag) < target) {
+                    if (signaled < next_store) signal_done();
+                    else if (next_store < t) do_store(next_store++);
+                    else __nanosleep(64);
+                }
+                tma::fence_async_all();
+            }
+            const int b = (int)(t % TMA_BUFFERS);
+            const TmaTileDesc d{role_a ? 1u : 0u, row, r, 0u};
+            hist[t % HIST] = d;
+            sm.desc[b] = d;
+            tma::mbar_arrive_expect_tx(&sm.full[b], TMA_TILE_BYTES);
+            constexpr int ES = sizeof(T) == 4 ? 1 : 2;
+            if (role_a) {
+                constexpr int ROWS = 1 << LG_N1;
+#pragma unroll
+                for (int r0 = 0; r0 < ROWS; r0 += BOX_A)
+                    tma::load_3d(sm.buf[b] + (size_t)r0 * L_A * sizeof(V), &map_x, (int)r * L_A * ES, r0, (int)row, &sm.full[b], pol_stream);
+            } else {
+                const long long wrow = a.ring ? row % a.ring : row;
+                constexpr int ROWS = 1 << LG_N2;
+#pragma unroll
+                for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
+                    tma::load_3d(sm.buf[b] + (size_t)r0 * L_B * sizeof(V), &map_w, (int)r * L_B * ES, r0, (int)wrow, &sm.full[b], pol_stream);
+            }
+            signal_done();
+        }
+        // no more tiles: tell both groups (one more buffer turn each), then drain
+        for (unsigned e = 0; e < TMA_GROUPS; ++e, ++t) {
+            while (next_store + TMA_BUFFERS <= t) do_store(next_store++);
+            signal_done();
+            const int b = (int)(t % TMA_BUFFERS);
+            sm.desc[b] = TmaTileDesc{0u, 0u, 0u, 1u};
+            tma::mbar_arrive(&sm.full[b]);
+        }
+        const unsigned last = t - TMA_GROUPS;       // tiles 0 .. last-1 were real
+        while (next_store < last) do_store(next_store++);
+        signal_done();
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int group = tid / TMA_GROUP_THREADS, gtid = tid % TMA_GROUP_THREADS;
+    const int bar_id = 1 + group;
+    for (unsigned t = (unsigned)group;; t += TMA_GROUPS) {
+        const int b = (int)(t % TMA_BUFFERS);
+        tma::mbar_wait(&sm.full[b], (t / TMA_BUFFERS) & 1);
+        const TmaTileDesc d = sm.desc[b];
+        if (d.exit) break;
+        V *buf = reinterpret_cast<V *>(sm.buf[b]);
+        if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id);
+        else TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id);
+        tma::fence_async_smem();
+        tma::mbar_arrive(&sm.ready[b]);
+    }
+}
+
+}  // namespace dscfft
+
+#endif  // !DSC_EMUL

@@ -1,0 +1,9 @@
+// Explicit instantiations: float TMA-fed four-step launches (fft_tma.cuh).
+#include <utility>
+#include "fft_dispatch.cuh"
+#if !defined(DSC_EMUL)
+namespace dscfft {
+DSC_DEFINE_TMA(float, true)
+DSC_DEFINE_TMA(float, false)
+}
+#endif

@@ -63,6 +63,10 @@ class ShardedFFT:
         wb = max(self.api.work_bytes(self.plan1, self.rows), self.api.work_bytes(self.plan2, self.cols),
                  self.api.work_bytes_axis(self.plan1, 1, self.rows), 256)
         self.work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+        # measurement hooks (bench.py): when `events` is a list, every exchange appends a (start, stop) pair of CUDA
+        # events recorded on the current stream around the all-to-all; `last_mode` names the exchange path taken
+        self.events = None
+        self.last_mode = None
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
@@ -132,6 +136,11 @@ class ShardedFFT:
             recv = torch.empty_like(send)                        # [q][k1_local][n2_local]
             slab = self.cols * self.rows
             in_place = self.plan2.lg_n2 != 0 and self.device.type == "cuda"
+            ev = None
+            if self.events is not None and self.device.type == "cuda":
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            self.last_mode = "blocking all_to_all (P-1 slabs, own slab stays)" if in_place else "blocking all_to_all_single"
             if in_place:
                 # the slab a rank would send to itself stays where it is: the exchange moves the P-1 others only,
                 # and the second transform reads that segment from the send buffer
@@ -142,6 +151,9 @@ class ShardedFFT:
                 dist.all_to_all(outs, ins, group=self.group)
             else:
                 dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+            if ev is not None:
+                ev[1].record()
+                self.events.append(ev)
             out = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
             # line k1_local is P segments of N2/P points, one per source rank: transformed where it lies when the
             # plan is a two-pass one (the first pass reads segmented rows), else un-interleaved first
