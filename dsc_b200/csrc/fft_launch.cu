@@ -324,7 +324,8 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     const long long tiles_a = n2 / te->l_a, tiles_b = n1 / te->l_b;
     if (rows * (tiles_a + tiles_b) >= 0x7fffffffLL) return 1;
     long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
-    const long long cap = (long long)(((size_t)64 << 20) / row_bytes) > 4 ? (long long)(((size_t)64 << 20) / row_bytes) : 4;
+    static const size_t ring_budget = [] { const char *e = getenv("DSC_TMA_RING_MB"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20; }();
+    const long long cap = (long long)(ring_budget / row_bytes) > 4 ? (long long)(ring_budget / row_bytes) : 4;
     if (ring > cap) ring = cap;
     if (ring >= rows) ring = 0;
     FourStepSync s{};

@@ -60,6 +60,15 @@ DSC_DEV bool mbar_try_wait(void *bar, unsigned parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+DSC_DEV bool mbar_test_wait(void *bar, unsigned parity) {       // never suspends
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 DSC_DEV void mbar_wait(void *bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
@@ -99,6 +108,7 @@ DSC_DEV void store_linear(void *gdst, const void *src, unsigned bytes, unsigned 
 DSC_DEV void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DSC_DEV void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DSC_DEV void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+DSC_DEV void store_wait_all_but_one() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 
 }  // namespace tma
 
@@ -107,7 +117,7 @@ constexpr int TMA_TILE_BYTES = 64 * 1024;
 constexpr int TMA_BUFFERS = 3;
 constexpr int TMA_GROUPS = 2;                 // consumer groups of TMA_GROUP_THREADS threads
 constexpr int TMA_GROUP_THREADS = 256;
-constexpr int TMA_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 32;     // + the producer warp
+constexpr int TMA_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 64;     // + the loader warp and the storer warp
 
 template <typename T> __host__ __device__ constexpr int tma_lg_e() { return sizeof(T) == 4 ? 5 : 4; }     // 32 / 16 points per thread
 template <typename T> __host__ __device__ constexpr int tma_tile_points() { return TMA_TILE_BYTES / (int)sizeof(cx<T>); }
@@ -136,7 +146,8 @@ template <typename T> struct TmaSmem {
     alignas(1024) unsigned char buf[TMA_BUFFERS][TMA_TILE_BYTES];
     V table[TMA_GROUPS][TABLE_MAX];
     unsigned long long full[TMA_BUFFERS];          // bytes of the tile have landed (producer + TMA -> consumers)
-    unsigned long long ready[TMA_BUFFERS];         // the finished tile lies in the buffer (consumers -> producer)
+    unsigned long long ready[TMA_BUFFERS];         // the finished tile lies in the buffer (consumers -> storer)
+    unsigned long long empty[TMA_BUFFERS];         // the store has read the buffer (storer -> loader)
     TmaTileDesc desc[TMA_BUFFERS];
 };
 
@@ -297,13 +308,16 @@ struct TmaTile {
 };
 
 // ---- the persistent launch --------------------------------------------------------------------------------
-// One block per SM: warps 0..15 are two consumer groups, warp 16 lane 0 is the producer.  The producer walks
-// the block's tile sequence t = 0, 1, 2, ...: tile t is transformed by group t % 2 in buffer t % 3.
-//   producer, tile t :  take a ticket -> store tile t-3 out of buffer t % 3 (when its group has finished it) and
-//                       wait until the copy has READ the buffer -> wait for the tile's dependency (all first-pass
-//                       tiles of the row; the second pass of the row that used the work row before) -> issue the
-//                       box loads -> wait for the stores issued so far to COMPLETE and publish their rows' counters.
-//   consumer, tile t :  wait full[t % 3] -> transform in place -> fence.proxy.async -> arrive on ready[t % 3].
+// One block per SM: warps 0..15 are two butterfly groups, lane 0 of warp 16 is the loader, lane 0 of warp 17 the
+// storer.  The block's tile sequence is t = 0, 1, 2, ...: tile t is transformed by group t % 2 in buffer t % 3.
+//   loader, tile t   :  take a ticket -> wait for the tile's dependency (all first-pass tiles of the row; the second
+//                       pass of the row that used the work row before) -> wait empty[t % 3] (the store of tile t - 3 has
+//                       read the buffer) -> descriptor + box loads, completion on full[t % 3].
+//   group, tile t    :  wait full[t % 3] -> transform in place -> fence.proxy.async -> arrive on ready[t % 3].
+//   storer, tile t   :  wait ready[t % 3] -> bulk store -> wait until it has READ the buffer -> arrive on empty[t % 3]
+//                       -> once the store before it has COMPLETED, publish that tile's row counter.  Whenever the
+//                       next tile is not ready yet it first completes and publishes everything outstanding, so no
+//                       other block (or this block's loader) waits on a counter longer than a store takes.
 template <typename T, int LG_N1, int LG_N2, bool FWD>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -323,6 +337,7 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         for (int b = 0; b < TMA_BUFFERS; ++b) {
             tma::mbar_init(&sm.full[b], 1);
             tma::mbar_init(&sm.ready[b], TMA_GROUP_THREADS);
+            tma::mbar_init(&sm.empty[b], 1);
         }
         tma::fence_barrier_init();
     }
@@ -330,98 +345,109 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
     const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
     if (tid >= TMA_GROUPS * TMA_GROUP_THREADS) {
-        // ------------------------------------------------------------------ producer
-        if (tid != TMA_GROUPS * TMA_GROUP_THREADS) return;
+        // ------------------------------------------------------------------ the two copy threads
+        const int warp = (tid - TMA_GROUPS * TMA_GROUP_THREADS) / 32;
+        if ((tid & 31) != 0) return;
         const unsigned long long pol_stream = tma::policy_evict_first(), pol_keep = tma::policy_evict_last();
-        constexpr unsigned HIST = TMA_BUFFERS + 1;  // tiles in the buffers + the one stored but not yet published
-        TmaTileDesc hist[HIST] = {};
-        unsigned next_store = 0, signaled = 0;      // tile sequence numbers
-
-        auto do_store = [&](const unsigned st) {
-            const int b = (int)(st % TMA_BUFFERS);
-            tma::mbar_wait(&sm.ready[b], (st / TMA_BUFFERS) & 1);
-            const TmaTileDesc d = hist[st % HIST];
-            if (d.role_a) {
-                // L_A contiguous lines W[q0 + l][k1] of the work row
-                const long long wrow = a.ring ? d.row % a.ring : d.row;
-                V *dst = (V *)a.work + ((wrow << LG_N2) + (long long)d.r * L_A << LG_N1);
-                tma::store_linear(dst, sm.buf[b], TMA_TILE_BYTES, pol_keep);
-            } else {
-                constexpr int ROWS = 1 << LG_N2;
-                constexpr int ES = sizeof(T) == 4 ? 1 : 2;          // double2 boxes are described in 8-byte elements
-#pragma unroll
-                for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
-                    tma::store_3d(&map_out, (int)d.r * L_B * ES, r0, (int)d.row, sm.buf[b] + (size_t)r0 * L_B * sizeof(V),
-                                  a.keep_out ? pol_keep : pol_stream);
-            }
-            tma::store_commit();
-            tma::store_wait_read();
-        };
-        auto signal_done = [&]() {
-            if (signaled == next_store) return;
-            tma::store_wait_all();
-            tma::fence_async_all();                 // async-proxy writes before the generic-proxy release below
-            for (; signaled < next_store; ++signaled) {
-                const TmaTileDesc d = hist[signaled % HIST];
-                dsc_signal_release((d.role_a ? s.a_done : s.b_done) + d.row);
-            }
-        };
-
-        unsigned pending = atomicAdd(s.ticket, 1u);
-        unsigned t = 0;
-        for (;; ++t) {
-            const unsigned ticket = pending;
-            if (ticket >= total) break;
-            pending = atomicAdd(s.ticket, 1u);
-            unsigned row, r;
-            bool role_a;
-            decode_ticket(s, ticket, role_a, row, r);
-            // the buffer: tile t - 3 has to leave first (its counters are published after this tile's loads are issued)
-            while (next_store + TMA_BUFFERS <= t) do_store(next_store++);
-            // the dependency; while it is open, finish the block's own earlier tiles (it may be one of them)
-            const unsigned *flag = nullptr;
-            unsigned target = 0;
-            if (!role_a) { flag = s.a_done + row; target = (unsigned)s.tiles_a; }
-            else if (s.ring && row >= (unsigned)s.ring) { flag = s.b_done + (row - s.ring); target = (unsigned)s.tiles_b; }
-            if (flag != nullptr) {
-                while (ld_acquire(flag) < target) {
-                    if (signaled < next_store) signal_done();
-                    else if (next_store < t) do_store(next_store++);
-                    else __nanosleep(64);
+        constexpr int ES = sizeof(T) == 4 ? 1 : 2;          // double2 boxes are described in 8-byte elements
+        if (warp == 0) {
+            // ---- loader: tickets, dependencies, box loads
+            unsigned pending = atomicAdd(s.ticket, 1u);
+            unsigned t = 0;
+            int exits_posted = 0;
+            for (;; ++t) {
+                const unsigned ticket = pending;
+                const bool exit = ticket >= total;
+                unsigned row = 0, r = 0;
+                bool role_a = false;
+                if (!exit) {
+                    pending = atomicAdd(s.ticket, 1u);
+                    decode_ticket(s, ticket, role_a, row, r);
+                    // the dependency: every first-pass tile of the row / the second pass of the row that used the
+                    // work row before.  The block's own earlier tiles are published by the storer, which never
+                    // waits for this thread.
+                    const unsigned *flag = nullptr;
+                    unsigned target = 0;
+                    if (!role_a) { flag = s.a_done + row; target = (unsigned)s.tiles_a; }
+                    else if (s.ring && row >= (unsigned)s.ring) { flag = s.b_done + (row - s.ring); target = (unsigned)s.tiles_b; }
+                    if (flag != nullptr) {
+                        while (ld_acquire(flag) < target) __nanosleep(64);
+                        tma::fence_async_all();
+                    }
                 }
-                tma::fence_async_all();
-            }
-            const int b = (int)(t % TMA_BUFFERS);
-            const TmaTileDesc d{role_a ? 1u : 0u, row, r, 0u};
-            hist[t % HIST] = d;
-            sm.desc[b] = d;
-            tma::mbar_arrive_expect_tx(&sm.full[b], TMA_TILE_BYTES);
-            constexpr int ES = sizeof(T) == 4 ? 1 : 2;
-            if (role_a) {
-                constexpr int ROWS = 1 << LG_N1;
+                // the buffer: the store of tile t - 3 has read it
+                const int b = (int)(t % TMA_BUFFERS);
+                if (t >= TMA_BUFFERS) tma::mbar_wait(&sm.empty[b], (t / TMA_BUFFERS - 1) & 1);
+                if (exit) {
+                    // no more tiles: one more turn for each group (and the storer), then leave
+                    sm.desc[b] = TmaTileDesc{0u, 0u, 0u, 1u};
+                    tma::mbar_arrive(&sm.full[b]);
+                    if (++exits_posted == TMA_GROUPS) break;
+                    continue;
+                }
+                sm.desc[b] = TmaTileDesc{role_a ? 1u : 0u, row, r, 0u};
+                tma::mbar_arrive_expect_tx(&sm.full[b], TMA_TILE_BYTES);
+                if (role_a) {
+                    constexpr int ROWS = 1 << LG_N1;
 #pragma unroll
-                for (int r0 = 0; r0 < ROWS; r0 += BOX_A)
-                    tma::load_3d(sm.buf[b] + (size_t)r0 * L_A * sizeof(V), &map_x, (int)r * L_A * ES, r0, (int)row, &sm.full[b], pol_stream);
-            } else {
-                const long long wrow = a.ring ? row % a.ring : row;
-                constexpr int ROWS = 1 << LG_N2;
+                    for (int r0 = 0; r0 < ROWS; r0 += BOX_A)
+                        tma::load_3d(sm.buf[b] + (size_t)r0 * L_A * sizeof(V), &map_x, (int)r * L_A * ES, r0, (int)row, &sm.full[b], pol_stream);
+                } else {
+                    const long long wrow = a.ring ? row % a.ring : row;
+                    constexpr int ROWS = 1 << LG_N2;
 #pragma unroll
-                for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
-                    tma::load_3d(sm.buf[b] + (size_t)r0 * L_B * sizeof(V), &map_w, (int)r * L_B * ES, r0, (int)wrow, &sm.full[b], pol_stream);
+                    for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
+                        tma::load_3d(sm.buf[b] + (size_t)r0 * L_B * sizeof(V), &map_w, (int)r * L_B * ES, r0, (int)wrow, &sm.full[b], pol_stream);
+                }
             }
-            signal_done();
+        } else {
+            // ---- storer: finished tiles leave; their rows' counters are published once the copies have completed
+            TmaTileDesc unpublished[2];
+            int n_unpublished = 0;
+            auto publish = [&](const int keep) {        // all but the `keep` most recent stores
+                if (n_unpublished <= keep) return;
+                if (keep == 0) tma::store_wait_all(); else tma::store_wait_all_but_one();
+                tma::fence_async_all();                 // async-proxy writes before the generic-proxy release below
+                for (int i = 0; i < n_unpublished - keep; ++i) {
+                    const TmaTileDesc d = unpublished[i];
+                    dsc_signal_release((d.role_a ? s.a_done : s.b_done) + d.row);
+                }
+                if (keep) unpublished[0] = unpublished[n_unpublished - 1];
+                n_unpublished = keep < n_unpublished ? keep : n_unpublished;
+            };
+            int exits = 0;
+            for (unsigned st = 0;; ++st) {
+                const int b = (int)(st % TMA_BUFFERS);
+                const unsigned par = (st / TMA_BUFFERS) & 1;
+                if (!tma::mbar_test_wait(&sm.ready[b], par)) {
+                    publish(0);                         // nothing to do anyway: other blocks may be waiting for these
+                    tma::mbar_wait(&sm.ready[b], par);
+                }
+                const TmaTileDesc d = sm.desc[b];
+                if (d.exit) {
+                    if (++exits == TMA_GROUPS) break;
+                    continue;
+                }
+                if (d.role_a) {
+                    // L_A contiguous lines W[q0 + l][k1] of the work row
+                    const long long wrow = a.ring ? d.row % a.ring : d.row;
+                    V *dst = (V *)a.work + ((wrow << LG_N2) + (long long)d.r * L_A << LG_N1);
+                    tma::store_linear(dst, sm.buf[b], TMA_TILE_BYTES, pol_keep);
+                } else {
+                    constexpr int ROWS = 1 << LG_N2;
+#pragma unroll
+                    for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
+                        tma::store_3d(&map_out, (int)d.r * L_B * ES, r0, (int)d.row, sm.buf[b] + (size_t)r0 * L_B * sizeof(V),
+                                      a.keep_out ? pol_keep : pol_stream);
+                }
+                tma::store_commit();
+                tma::store_wait_read();
+                tma::mbar_arrive(&sm.empty[b]);         // the loader may refill the buffer (and overwrite desc[b])
+                unpublished[n_unpublished++] = d;
+                publish(1);
+            }
+            publish(0);
         }
-        // no more tiles: tell both groups (one more buffer turn each), then drain
-        for (unsigned e = 0; e < TMA_GROUPS; ++e, ++t) {
-            while (next_store + TMA_BUFFERS <= t) do_store(next_store++);
-            signal_done();
-            const int b = (int)(t % TMA_BUFFERS);
-            sm.desc[b] = TmaTileDesc{0u, 0u, 0u, 1u};
-            tma::mbar_arrive(&sm.full[b]);
-        }
-        const unsigned last = t - TMA_GROUPS;       // tiles 0 .. last-1 were real
-        while (next_store < last) do_store(next_store++);
-        signal_done();
         return;
     }
 
@@ -432,7 +458,7 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int b = (int)(t % TMA_BUFFERS);
         tma::mbar_wait(&sm.full[b], (t / TMA_BUFFERS) & 1);
         const TmaTileDesc d = sm.desc[b];
-        if (d.exit) break;
+        if (d.exit) { tma::mbar_arrive(&sm.ready[b]); break; }
         V *buf = reinterpret_cast<V *>(sm.buf[b]);
         if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id);
         else TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id);
