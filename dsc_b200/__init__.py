@@ -96,6 +96,18 @@ def _load():
         getattr(L, name).restype = _TP
         getattr(L, name).argtypes = [C.c_void_p, _TP]
     L.dsc_tensor_get_slice.restype = _TP
+    L.dsc_tensor_set_slice.restype = None
+    L.dsc_cast.restype = _TP
+    L.dsc_cast.argtypes = [C.c_void_p, _TP, C.c_uint8]
+    L.dsc_transpose.restype = _TP
+    for name in ("dsc_fftfreq", "dsc_rfftfreq"):
+        getattr(L, name).restype = _TP
+        getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint8]
+    for name in ("dsc_irfft_keep",):
+        getattr(L, name).restype = _TP
+        getattr(L, name).argtypes = [C.c_void_p, _TP, _TP, C.c_int, C.c_int, C.c_int]
+    L.dsc_fft_filter_keep.restype = _TP
+    L.dsc_fft_filter_keep.argtypes = [C.c_void_p, _TP, _TP, _TP, C.c_int, C.c_int, C.c_int]
     L.dsc_traces_record.argtypes = [C.c_void_p, C.c_bool]
     L.dsc_dump_traces.argtypes = [C.c_void_p, C.c_char_p]
     L.dsc_clear_traces.argtypes = [C.c_void_p]
@@ -197,7 +209,8 @@ class Tensor:
     def __truediv__(self, other: "Tensor") -> "Tensor":
         return true_div(self, other)
 
-    def __getitem__(self, item) -> "Tensor":
+    @staticmethod
+    def _slices(item):
         items = item if isinstance(item, tuple) else (item,)
         args = []
         for it in items:
@@ -207,7 +220,24 @@ class Tensor:
                                     VALUE_NONE if it.step is None else it.step))
             else:
                 args.append(_CSlice(int(it), int(it), int(it)))     # single-index convention
+        return args
+
+    def __getitem__(self, item) -> "Tensor":
+        args = self._slices(item)
         return Tensor(_load().dsc_tensor_get_slice(_get_ctx(), self._ptr, C.c_int(len(args)), *args))
+
+    def __setitem__(self, item, value) -> None:
+        """x[slices] = value (python/dsc/tensor.py:220-237 -> dsc_tensor_set_slice, dsc/src/dsc.cpp:1108-1169)."""
+        args = self._slices(item)
+        v = value if isinstance(value, Tensor) else from_numpy(np.asarray(value, dtype=self.dtype))
+        _load().dsc_tensor_set_slice(_get_ctx(), self._ptr, v._ptr, C.c_int(len(args)), *args)
+
+    def cast(self, np_dtype) -> "Tensor":
+        """dsc_cast (dsc/src/dsc.cpp:587-597); returns self when the dtype already matches, like the reference."""
+        ptr = _load().dsc_cast(_get_ctx(), self._ptr, _NP2DSC[np.dtype(np_dtype)])
+        if C.addressof(ptr.contents) == C.addressof(self._ptr.contents):
+            return self
+        return Tensor(ptr)
 
 
 def from_numpy(a: np.ndarray) -> Tensor:
@@ -300,6 +330,36 @@ def imag(x) -> Tensor:
 
 def conj(x) -> Tensor:
     return _unary_new("dsc_conj", x)
+
+
+def transpose(x, axes=None) -> Tensor:
+    """dsc_transpose (dsc/src/dsc.cpp:764-827): axes=None reverses the dims."""
+    x = _as_tensor(x)
+    axes = tuple(axes) if axes is not None else ()
+    return Tensor(_load().dsc_transpose(_get_ctx(), x._ptr, C.c_int(len(axes)), *[C.c_int(int(a)) for a in axes]))
+
+
+def fftfreq(n: int, d: float = 1.0, dtype=np.float64) -> Tensor:
+    return Tensor(_load().dsc_fftfreq(_get_ctx(), int(n), float(d), _NP2DSC[np.dtype(dtype)]))
+
+
+def rfftfreq(n: int, d: float = 1.0, dtype=np.float64) -> Tensor:
+    return Tensor(_load().dsc_rfftfreq(_get_ctx(), int(n), float(d), _NP2DSC[np.dtype(dtype)]))
+
+
+def irfft_keep(x, keep: int, out: Optional[Tensor] = None, n: int = -1) -> Tensor:
+    """irfft along the last axis storing only the first `keep` samples of every line: the README's
+    irfft(...)[:output_length] (README.md:130-133) with the crop fused into the inverse kernel's store."""
+    x = _as_tensor(x)
+    ptr = _load().dsc_irfft_keep(_get_ctx(), x._ptr, out._ptr if out is not None else None, int(n), -1, int(keep))
+    return Tensor(ptr, view=out is not None)
+
+
+def fft_filter_keep(x, B, keep: int, out: Optional[Tensor] = None, n: int = -1) -> Tensor:
+    """fft_filter storing only the first `keep` samples of every line (crop fused into the kernel's store)."""
+    x, B = _as_tensor(x), _as_tensor(B)
+    ptr = _load().dsc_fft_filter_keep(_get_ctx(), x._ptr, B._ptr, out._ptr if out is not None else None, int(n), -1, int(keep))
+    return Tensor(ptr, view=out is not None)
 
 
 def fft_filter(x, B, out: Optional[Tensor] = None, n: int = -1, axis: int = -1) -> Tensor:

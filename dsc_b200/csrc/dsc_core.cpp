@@ -295,7 +295,7 @@ bool dsc_try_device_binary(dsc_ctx *ctx, const int op, const dsc_tensor *xa, con
     // round trip through the host: only taken when an operand is already device-resident, so the default
     // (strict) mode never gets here.  Same dtype everywhere; xb same shape, one row, or one element.
     if (!ctx->has_device || ctx->residency < 1) return false;
-    if (xa->dtype != out->dtype || xb->dtype != out->dtype) return false;
+    const bool mixed = xa->dtype != out->dtype || xb->dtype != out->dtype;    // promoted in registers (dsc_dtype.h:73-78)
     if (!((xa->buffer->flags | xb->buffer->flags) & DSC_BUF_DEV_VALID)) return false;
     if (memcmp(xa->shape, out->shape, sizeof(out->shape)) != 0) return false;
     const bool same = memcmp(xb->shape, out->shape, sizeof(out->shape)) == 0;
@@ -311,8 +311,9 @@ bool dsc_try_device_binary(dsc_ctx *ctx, const int op, const dsc_tensor *xa, con
     const i64 cols = out->shape[DSC_MAX_DIMS - 1];
     const i64 rows = cols > 0 ? out->ne / cols : 0;
     const int b_mode = same ? 1 : row ? 0 : 2;
-    if (dsc_cuda_binary(op, da, db, dout, out->dtype, rows, cols, b_mode, dscdev::stream(0)) != 0)
-        DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    const int rc = mixed ? dsc_cuda_binary_mixed(op, da, xa->dtype, db, xb->dtype, dout, rows, cols, b_mode, dscdev::stream(0))
+                         : dsc_cuda_binary(op, da, db, dout, out->dtype, rows, cols, b_mode, dscdev::stream(0));
+    if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
     result_on_device(ctx, out, dout);
     xa->buffer->busy = xb->buffer->busy = out->buffer->busy = 0;
     return true;
@@ -329,6 +330,68 @@ bool dsc_try_device_unary(dsc_ctx *ctx, const int op, const dsc_tensor *x, dsc_t
     if (dsc_cuda_unary(op, dx, x->dtype, dout, x->ne, dscdev::stream(0)) != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
     result_on_device(ctx, out, dout);
     x->buffer->busy = out->buffer->busy = 0;
+    return true;
+}
+
+bool dsc_try_device_cast(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out) noexcept {
+    if (!ctx->has_device || ctx->residency < 1) return false;
+    if (!(x->buffer->flags & DSC_BUF_DEV_VALID) || x->buffer == out->buffer || x->ne == 0) return false;
+    if (out->buffer->flags & DSC_BUF_SCRATCH) return false;        // promotion temporaries of host loops stay on the host
+    const void *dx = operand_on_device(ctx, x);
+    out->buffer->busy = 1;
+    void *dout = dsc_dev_ptr(ctx, out->buffer);
+    if (dsc_cuda_cast(dx, x->dtype, dout, out->dtype, x->ne, dscdev::stream(0)) != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    result_on_device(ctx, out, dout);
+    x->buffer->busy = out->buffer->busy = 0;
+    return true;
+}
+
+bool dsc_try_device_gather(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, const int shape[DSC_MAX_DIMS],
+                           const i64 stride[DSC_MAX_DIMS], const i64 base) noexcept {
+    if (!ctx->has_device || ctx->residency < 1) return false;
+    if (!(x->buffer->flags & DSC_BUF_DEV_VALID) || x->buffer == out->buffer || out->ne == 0) return false;
+    const void *dx = operand_on_device(ctx, x);
+    out->buffer->busy = 1;
+    void *dout = dsc_dev_ptr(ctx, out->buffer);
+    const int es = (int) DSC_DTYPE_SIZE[x->dtype];
+    // a swap of the last two dims of a batch of matrices: the tiled transpose (coalesced on both sides)
+    const bool swap_last = base == 0 && stride[3] == (i64) shape[3 - 1] && stride[2] == 1 &&
+                           stride[1] == (i64) shape[2] * shape[3] && stride[0] == (i64) shape[1] * shape[2] * shape[3];
+    int rc;
+    if (swap_last && shape[2] > 1 && shape[3] > 1)
+        rc = dsc_cuda_transpose_batched(dx, dout, (i64) shape[0] * shape[1], shape[3], shape[2], es, dscdev::stream(0));
+    else
+        rc = dsc_cuda_gather(dx, dout, es, shape, (const int64_t *) stride, base, dscdev::stream(0));
+    if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    result_on_device(ctx, out, dout);
+    x->buffer->busy = out->buffer->busy = 0;
+    return true;
+}
+
+bool dsc_try_device_scatter(dsc_ctx *ctx, dsc_tensor *xa, const dsc_tensor *xb, const int shape[DSC_MAX_DIMS],
+                            const i64 stride[DSC_MAX_DIMS], const i64 base) noexcept {
+    // only when xa's current contents live on the device alone (lazy mode): otherwise the host loop keeps the host
+    // copy current and just invalidates the mirror
+    if (!ctx->has_device || ctx->residency < 2) return false;
+    dsc_tensor_buffer *ba = xa->buffer;
+    if (!(ba->flags & DSC_BUF_DEV_VALID) || !(ba->flags & DSC_BUF_HOST_STALE) || ba == xb->buffer || xb->ne == 0) return false;
+    finish_download(ba);
+    ba->busy = 1;
+    void *da = dsc_dev_ptr(ctx, ba);
+    const void *db = operand_on_device(ctx, xb);
+    if (dsc_cuda_scatter(da, db, (int) DSC_DTYPE_SIZE[xa->dtype], shape, (const int64_t *) stride, base, xb->ne, dscdev::stream(0)) != 0)
+        DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    ba->busy = xb->buffer->busy = 0;
+    return true;                                                // xa stays device-valid, host-stale
+}
+
+bool dsc_try_device_fftfreq(dsc_ctx *ctx, dsc_tensor *out, const int n, const f64 d, const bool rfft) noexcept {
+    if (!ctx->has_device || ctx->residency < 1) return false;
+    out->buffer->busy = 1;
+    void *dout = dsc_dev_ptr(ctx, out->buffer);
+    if (dsc_cuda_fftfreq(dout, out->dtype, n, d, rfft ? 1 : 0, dscdev::stream(0)) != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
+    result_on_device(ctx, out, dout);
+    out->buffer->busy = 0;
     return true;
 }
 
@@ -573,6 +636,7 @@ struct xform_job {
     const dsc_tensor *spectrum;     // XF_FILTER: B = rfft(b), broadcast over lines
     i64 outer, inner;
     int x_n, out_n;
+    int keep;                       // XF_IRFFT / XF_FILTER: store only the first `keep` samples per line (0 = all); out_n == keep
     // composed paths (see launch_chunk): two device temporaries and, for huge plans, the sub-plans
     byte *tmp_a, *tmp_b;
     const dsc_fft_plan *sub1, *sub2;
@@ -657,12 +721,14 @@ void launch_chunk(dsc_ctx *ctx, const xform_job &j, const byte *dx, byte *dout, 
             rc = dsc_cuda_rfft(&j.plan->cu, src, dst, rows, j.x_n, j.inner, work, work_bytes, s);
             break;
         case XF_IRFFT:
-            rc = dsc_cuda_irfft(&j.plan->cu, src, dst, rows, j.x_n, j.inner, work, work_bytes, s);
+            rc = j.keep ? dsc_cuda_irfft_keep(&j.plan->cu, src, dst, rows, j.x_n, j.keep, work, work_bytes, s)
+                        : dsc_cuda_irfft(&j.plan->cu, src, dst, rows, j.x_n, j.inner, work, work_bytes, s);
             break;
         case XF_FILTER:
             // rfft -> spectrum product -> irfft without the spectrum ever leaving the device (one kernel for
             // orders that fit shared memory)
-            rc = dsc_cuda_filter(&j.plan->cu, src, dsc_dev_ptr(ctx, j.spectrum->buffer), dst, rows, j.x_n, work, work_bytes, s);
+            rc = j.keep ? dsc_cuda_filter_keep(&j.plan->cu, src, dsc_dev_ptr(ctx, j.spectrum->buffer), dst, rows, j.x_n, j.keep, work, work_bytes, s)
+                        : dsc_cuda_filter(&j.plan->cu, src, dsc_dev_ptr(ctx, j.spectrum->buffer), dst, rows, j.x_n, work, work_bytes, s);
             break;
     }
     if (rc != 0) DSC_LOG_FATAL("%s", dsc_cuda_last_error());
@@ -971,6 +1037,96 @@ dsc_tensor *dsc_rfft(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, dsc_tensor 
 }
 dsc_tensor *dsc_irfft(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, dsc_tensor *DSC_RESTRICT out, const int n, const int axis) noexcept {
     return dsc_internal_rfft(ctx, x, out, n, axis, false);
+}
+
+namespace {
+// The crop of README.md:130-133 fused into the store, where the launch layer can do it (orders of one shared-memory
+// pass); else the full transform followed by dsc_tensor_get_slice's device crop.
+dsc_tensor *crop_last_axis(dsc_ctx *ctx, dsc_tensor *full, dsc_tensor *out, const int keep) noexcept {
+    dsc_slice sl[DSC_MAX_DIMS];
+    for (int i = 0; i < full->n_dim; ++i) sl[i] = dsc_slice{DSC_VALUE_NONE, DSC_VALUE_NONE, 1};
+    sl[full->n_dim - 1] = dsc_slice{0, keep, 1};
+    dsc_tensor *cropped = full->n_dim == 1 ? dsc_tensor_get_slice(ctx, full, 1, sl[0])
+                          : full->n_dim == 2 ? dsc_tensor_get_slice(ctx, full, 2, sl[0], sl[1])
+                          : full->n_dim == 3 ? dsc_tensor_get_slice(ctx, full, 3, sl[0], sl[1], sl[2])
+                                             : dsc_tensor_get_slice(ctx, full, 4, sl[0], sl[1], sl[2], sl[3]);
+    dsc_tensor_free(ctx, full);
+    if (out == nullptr) return cropped;
+    DSC_ASSERT(out->dtype == cropped->dtype && out->ne == cropped->ne);
+    dsc_host_needed(ctx, cropped);
+    memcpy(out->data, cropped->data, (usize) cropped->ne * DSC_DTYPE_SIZE[cropped->dtype]);
+    dsc_host_written(out->buffer);
+    dsc_tensor_free(ctx, cropped);
+    return out;
+}
+}  // namespace
+
+dsc_tensor *dsc_irfft_keep(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, dsc_tensor *DSC_RESTRICT out, const int n,
+                           const int axis, const int keep) noexcept {
+    DSC_ASSERT(x != nullptr);
+    char args[512];
+    fft_trace_args(args, sizeof(args), "IRFFT", n, axis, x, out);
+    dsc_span span("dsc_internal_rfft", "op;fft", args);
+    dsc_require_device(ctx, "dsc_irfft_keep");
+    const int axis_idx = dsc_tensor_dim(x, axis);
+    DSC_ASSERT(axis_idx == DSC_MAX_DIMS - 1);               // last axis only
+    const int x_n = x->shape[axis_idx];
+    const int order = dsc_pow2_n((n > 0 ? n : x_n) - 1);
+    DSC_ASSERT(order > 0);
+    DSC_ASSERT(keep > 0 && keep <= 2 * order);
+    dsc_dtype out_dtype;
+    if (x->dtype == C32) out_dtype = F32;
+    else if (x->dtype == C64) out_dtype = F64;
+    else DSC_LOG_FATAL("IRFFT input must be complex");
+    const dsc_fft_plan *plan = dsc_plan_fft(ctx, order, REAL, x->dtype);
+    if (plan->cu.lg_n2 != 0 || keep == 2 * order) {
+        dsc_tensor *full = dsc_internal_rfft(ctx, x, nullptr, n, axis, false);
+        return keep == 2 * order && out == nullptr ? full : crop_last_axis(ctx, full, out, keep);
+    }
+    out = make_out(ctx, x, out, axis_idx, keep, out_dtype);
+    xform_job j{};
+    j.scratch_capacity = ctx->dev_scratch.capacity;
+    j.kind = XF_IRFFT;
+    j.plan = plan;
+    j.x = x; j.out = out;
+    j.x_n = x_n; j.out_n = keep; j.keep = keep;
+    split_axis(x, axis_idx, &j.outer, &j.inner);
+    if (x->ne > 0) run_job(ctx, j);
+    return out;
+}
+
+dsc_tensor *dsc_fft_filter_keep(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const dsc_tensor *DSC_RESTRICT B,
+                                dsc_tensor *DSC_RESTRICT out, const int n, const int axis, const int keep) noexcept {
+    DSC_ASSERT(x != nullptr);
+    DSC_ASSERT(B != nullptr);
+    const int axis_idx = dsc_tensor_dim(x, axis);
+    DSC_ASSERT(axis_idx == DSC_MAX_DIMS - 1);
+    const int x_n = x->shape[axis_idx];
+    const int order = dsc_pow2_n(n > 0 ? n : x_n) >> 1;
+    DSC_ASSERT(order > 0);
+    DSC_ASSERT(keep > 0 && keep <= 2 * order);
+    if (x->dtype != F32 && x->dtype != F64) DSC_LOG_FATAL("filter input must be real");
+    const dsc_fft_plan *plan = dsc_plan_fft(ctx, order, REAL, x->dtype);
+    if (plan->cu.lg_n2 != 0 || keep == 2 * order) {
+        dsc_tensor *full = dsc_fft_filter(ctx, x, B, nullptr, n, axis);
+        return keep == 2 * order && out == nullptr ? full : crop_last_axis(ctx, full, out, keep);
+    }
+    char args[512];
+    fft_trace_args(args, sizeof(args), "FILTER", n, axis, x, out);
+    dsc_span span("dsc_fft_filter", "op;fft", args);
+    dsc_require_device(ctx, "dsc_fft_filter_keep");
+    DSC_ASSERT(B->dtype == (x->dtype == F32 ? C32 : C64));
+    DSC_ASSERT(B->ne == order + 1);
+    out = make_out(ctx, x, out, axis_idx, keep, x->dtype);
+    xform_job j{};
+    j.scratch_capacity = ctx->dev_scratch.capacity;
+    j.kind = XF_FILTER;
+    j.plan = plan;
+    j.x = x; j.out = out; j.spectrum = B;
+    j.x_n = x_n; j.out_n = keep; j.keep = keep;
+    split_axis(x, axis_idx, &j.outer, &j.inner);
+    if (x->ne > 0) run_job(ctx, j);
+    return out;
 }
 
 // out = irfft(rfft(x, n) * B) along the LAST axis; B holds order+1 bins (e.g. dsc_rfft(b, n)).

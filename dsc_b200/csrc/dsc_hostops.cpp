@@ -65,6 +65,7 @@ struct walker {
 };
 
 void copy_cast(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out) noexcept {
+    if (dsc_try_device_cast(ctx, x, out)) return;               // device-resident data is converted where it lies
     dsc_host_needed(ctx, x);
     by_dtype(x->dtype, [&](auto *tx) {
         using Tx = std::remove_pointer_t<decltype(tx)>;
@@ -227,7 +228,6 @@ dsc_tensor *dsc_transpose(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const 
         }
         va_end(args);
     }
-    dsc_host_needed(ctx, x);
     // output dim i takes input dim perm[i]; walk the output in order, gather through permuted strides
     int shape[DSC_MAX_DIMS] = {1, 1, 1, 1}, stride[DSC_MAX_DIMS] = {0, 0, 0, 0};
     for (int i = 0; i < x->n_dim; ++i) {
@@ -236,6 +236,14 @@ dsc_tensor *dsc_transpose(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const 
         stride[dst] = x->stride[src];
     }
     dsc_tensor *out = dsc_new_tensor(ctx, x->n_dim, &shape[DSC_MAX_DIMS - x->n_dim], x->dtype);
+    {
+        // leading dims of extent 1 get the stride a contiguous tensor would have, so the launch layer recognises a
+        // plain swap of the last two dims
+        i64 st[DSC_MAX_DIMS];
+        for (int d = 0; d < DSC_MAX_DIMS; ++d) st[d] = d < DSC_MAX_DIMS - x->n_dim ? (i64) x->ne : (i64) stride[d];
+        if (dsc_try_device_gather(ctx, x, out, shape, st, 0)) return out;
+    }
+    dsc_host_needed(ctx, x);
     const usize es = DSC_DTYPE_SIZE[x->dtype];
     walker w(shape);
     for (int i = 0; i < out->ne; ++i, w.step())
@@ -299,6 +307,18 @@ void read_slices(std::va_list args, const int n, dsc_slice *dst) noexcept {
 }
 
 void assign_selected(dsc_ctx *ctx, dsc_tensor *xa, const dsc_tensor *xb, const span1 *sp) noexcept {
+    {
+        // xa lives on the device only (lazy residency): write the selection there instead of downloading all of xa
+        int gshape[DSC_MAX_DIMS] = {1, 1, 1, 1};
+        i64 gstride[DSC_MAX_DIMS] = {0, 0, 0, 0}, gbase = 0;
+        for (int i = 0; i < xa->n_dim; ++i) {
+            const int d = dsc_tensor_dim(xa, i);
+            gshape[d] = sp[i].count;
+            gstride[d] = (i64) sp[i].step * xa->stride[d];
+            gbase += (i64) sp[i].start * xa->stride[d];
+        }
+        if (dsc_try_device_scatter(ctx, xa, xb, gshape, gstride, gbase)) return;
+    }
     dsc_host_needed(ctx, xa);
     dsc_host_needed(ctx, xb);
     const usize es = DSC_DTYPE_SIZE[xa->dtype];
@@ -369,6 +389,18 @@ dsc_tensor *dsc_tensor_get_slice(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x,
         last_axis_crop = last_axis_crop && !sp[i].collapse && sp[i].start == 0 && sp[i].step == 1 &&
                          sp[i].count == x->shape[dsc_tensor_dim(x, i)];
     if (last_axis_crop && dsc_try_device_crop(ctx, x, out, sp[x->n_dim - 1].start, sp[x->n_dim - 1].count)) return out;
+    {
+        // any other selection of device-resident data: gathered on the device
+        int gshape[DSC_MAX_DIMS] = {1, 1, 1, 1};
+        i64 gstride[DSC_MAX_DIMS] = {0, 0, 0, 0}, gbase = 0;
+        for (int i = 0; i < x->n_dim; ++i) {
+            const int d = dsc_tensor_dim(x, i);
+            gshape[d] = sp[i].count;
+            gstride[d] = (i64) sp[i].step * x->stride[d];
+            gbase += (i64) sp[i].start * x->stride[d];
+        }
+        if (dsc_try_device_gather(ctx, x, out, gshape, gstride, gbase)) return out;
+    }
 
     dsc_host_needed(ctx, x);
     const usize es = DSC_DTYPE_SIZE[x->dtype];
@@ -760,6 +792,7 @@ dsc_tensor *dsc_fftfreq(dsc_ctx *ctx, const int n, const f64 d, const dsc_dtype 
     DSC_ASSERT(n > 0);
     if (dtype != F32 && dtype != F64) DSC_LOG_FATAL("dtype must be real");
     dsc_tensor *out = dsc_tensor_1d(ctx, dtype, n);
+    if (dsc_try_device_fftfreq(ctx, out, n, d, false)) return out;
     // [0, 1, .., ceil(n/2)-1, -floor(n/2), .., -1] / (n d)
     const int pos = (n + 1) / 2;
     by_dtype(dtype, [&](auto *t) {
@@ -778,6 +811,7 @@ dsc_tensor *dsc_rfftfreq(dsc_ctx *ctx, const int n, const f64 d, const dsc_dtype
     if (dtype != F32 && dtype != F64) DSC_LOG_FATAL("dtype must be real");
     const int bins = n / 2 + 1;
     dsc_tensor *out = dsc_tensor_1d(ctx, dtype, bins);
+    if (dsc_try_device_fftfreq(ctx, out, n, d, true)) return out;
     by_dtype(dtype, [&](auto *t) {
         using T = std::remove_pointer_t<decltype(t)>;
         if constexpr (!is_cplx<T>::value) {

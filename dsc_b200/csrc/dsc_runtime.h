@@ -131,6 +131,20 @@ void dsc_host_needed(dsc_ctx *ctx, const dsc_tensor *x) noexcept;               
 bool dsc_try_device_binary(dsc_ctx *ctx, int op, const dsc_tensor *xa, const dsc_tensor *xb, dsc_tensor *out) noexcept;
 bool dsc_try_device_unary(dsc_ctx *ctx, int op, const dsc_tensor *x, dsc_tensor *out) noexcept;
 
+// The rest of SURVEY.md 8(f) on the device, taken when the operand is device-resident (residency >= 1); each returns
+// false when the host loop should run instead:
+//   cast      dsc_cast, any dtype pair (dsc.cpp:587-597, cast_op dsc_ops.h:12-44)
+//   gather    out (dense) = x viewed through permuted / stepped strides: dsc_transpose (dsc.cpp:764-827) and
+//             dsc_tensor_get_slice (:950-1007); shape[] are out's extents, stride[] / base x's element strides
+//   scatter   xa's selected elements = xb (recycled when shorter): dsc_tensor_set_slice / set_idx (:1108-1169)
+//   fftfreq   dsc_fftfreq / dsc_rfftfreq filled on the device (:2262-2339)
+bool dsc_try_device_cast(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out) noexcept;
+bool dsc_try_device_gather(dsc_ctx *ctx, const dsc_tensor *x, dsc_tensor *out, const int shape[DSC_MAX_DIMS],
+                           const i64 stride[DSC_MAX_DIMS], i64 base) noexcept;
+bool dsc_try_device_scatter(dsc_ctx *ctx, dsc_tensor *xa, const dsc_tensor *xb, const int shape[DSC_MAX_DIMS],
+                            const i64 stride[DSC_MAX_DIMS], i64 base) noexcept;
+bool dsc_try_device_fftfreq(dsc_ctx *ctx, dsc_tensor *out, int n, f64 d, bool rfft) noexcept;
+
 // Crop along the last axis of a tensor whose current contents live only on the device (residency 2): download
 // just the kept columns [start, start + count) of every row into `out` (the README's y[:output_length] after
 // irfft, README.md:133).  Returns false when the generic host path should run.

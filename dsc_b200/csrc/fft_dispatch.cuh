@@ -11,6 +11,7 @@
 #include <utility>
 #include "fft_kernels.cuh"
 #include "fft_tma.cuh"
+#include "fft_cluster.cuh"
 
 namespace dscfft {
 
@@ -186,6 +187,47 @@ template <> TmaEntry *tma_entry<double, false>(int, int);
 #define DSC_TMA_MAKE_false_float(A, B) make_tma<float, false, A, B>(),
 #define DSC_TMA_MAKE_true_double(A, B) make_tma<double, true, A, B>(),
 #define DSC_TMA_MAKE_false_double(A, B) make_tma<double, false, A, B>(),
+#endif
+
+// ---- one line per thread-block cluster (fft_cluster.cuh) --------------------------------------------------------
+#if !defined(DSC_EMUL)
+struct ClusterEntry {
+    void (*fn)(const CUtensorMap, const CUtensorMap, const ClusterArgs);
+    int lg_n1, lg_n2, l, lp, blocks, box_a, box_b, smem;
+    int state;            // 0 = not configured yet, 1 = usable, -1 = this device cannot co-schedule the cluster
+};
+
+template <typename T, bool FWD, int LG_N1, int LG_N2>
+ClusterEntry make_cluster() {
+    ClusterEntry e;
+    e.fn = fft_cluster<T, LG_N1, LG_N2, FWD>;
+    e.lg_n1 = LG_N1; e.lg_n2 = LG_N2;
+    e.l = tma_tile_points<T>() >> LG_N1;
+    e.blocks = (1 << LG_N2) / e.l;
+    e.lp = (1 << LG_N1) / e.blocks;
+    e.box_a = tma_box_rows(LG_N1); e.box_b = tma_box_rows(LG_N2);
+    e.smem = (int)sizeof(ClusterSmem<T, LG_N1>) + 1024;
+    e.state = 0;
+    return e;
+}
+
+// complex64 lines of 2^14 (2 blocks), 2^15 (4), 2^16 (8) and 2^17 (16 blocks: non-portable cluster size) points
+#define DSC_CLUSTER_PAIRS_float(X) X(7, 7) X(8, 7) X(8, 8) X(9, 8)
+
+template <typename T, bool FWD> ClusterEntry *cluster_entry(int lg_n1, int lg_n2);
+template <> ClusterEntry *cluster_entry<float, true>(int, int);
+template <> ClusterEntry *cluster_entry<float, false>(int, int);
+template <> inline ClusterEntry *cluster_entry<double, true>(int, int) { return nullptr; }
+template <> inline ClusterEntry *cluster_entry<double, false>(int, int) { return nullptr; }
+
+#define DSC_DEFINE_CLUSTER(T, FWD)                                                         \
+    template <> ClusterEntry *cluster_entry<T, FWD>(int lg_n1, int lg_n2) {                \
+        static ClusterEntry table[] = {DSC_CLUSTER_PAIRS_##T(DSC_CLUSTER_MAKE_##FWD##_##T)}; \
+        for (auto &e : table) if (e.lg_n1 == lg_n1 && e.lg_n2 == lg_n2) return &e;        \
+        return nullptr;                                                                    \
+    }
+#define DSC_CLUSTER_MAKE_true_float(A, B) make_cluster<float, true, A, B>(),
+#define DSC_CLUSTER_MAKE_false_float(A, B) make_cluster<float, false, A, B>(),
 #endif
 
 // ---- two-pass transforms along a non-last axis (four_step_columns) --------------------------------------------

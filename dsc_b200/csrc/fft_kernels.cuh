@@ -91,6 +91,8 @@ struct FftArgs {
     long long seg_self_delta;   // exchange that never left this GPU; element offset of that buffer from x
     int keep_out;         // four-step second pass: 1 = a later kernel re-reads the output soon (plain stores, the
                           // rows stay in L2); 0 = streaming stores
+    int out_take;         // MODE_C2R / MODE_FILTER: store only the first out_take real samples of every line (0 = all):
+                          // the README's irfft(...)[:output_length] crop (README.md:130-133) fused into the store
 };
 
 template <int LG_N, int LG_E> struct Sched {
@@ -574,7 +576,14 @@ DSC_DEV void fft_lines_body(const FftArgs &a, const long long block, unsigned ch
         // N complex = 2N reals; go is in REAL elements
         if (active) {
             T *__restrict__ orl = (T *)a.out + obase + ooff0;
-            if (a.packed_out) {
+            if (a.out_take) {
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    const int r0 = 2 * (t + c * TT);
+                    if (r0 < a.out_take) orl[c * ostep] = v[c].x;
+                    if (r0 + 1 < a.out_take) orl[c * ostep + a.go_pstride] = v[c].y;
+                }
+            } else if (a.packed_out) {
 #pragma unroll
                 for (int c = 0; c < E; ++c) __stcs((V *)(orl + c * ostep), v[c]);
             } else {

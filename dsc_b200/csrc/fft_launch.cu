@@ -205,7 +205,7 @@ int launch_lines(KernelEntry *table, int lg_n, const FftArgs &a_in, void *stream
         const size_t vec = 2 * real_bytes;
         a.packed_in = real_bytes && a.gi_pstride == 1 && a.gi.estride == 2 && a.inner == 1 && a.gi.ostride % 2 == 0 &&
                       (uintptr_t)a.x % vec == 0;
-        a.packed_out = real_bytes && a.go_pstride == 1 && a.go.estride == 2 && a.inner == 1 && a.go.ostride % 2 == 0 &&
+        a.packed_out = real_bytes && !a.out_take && a.go_pstride == 1 && a.go.estride == 2 && a.inner == 1 && a.go.ostride % 2 == 0 &&
                        (uintptr_t)a.out % vec == 0;
     }
     if (a.lines % e.lpb != 0) a.no_limit = 0;
@@ -370,6 +370,78 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
     return check_launch("four_step_tma");
 }
+// Which line lengths (log2) go to the cluster kernel.  Measured on B200 (profiles/r2_two_pass_lengths.md): it reads and
+// writes exactly the algorithmic bytes, but with two 256-thread blocks per SM and two cluster barriers per line it is
+// latency-bound -- 3.16 TB/s at 2^15 (TMA-fed two-pass launch: 3.0), 2.7 at 2^16 (3.0), 2.2 at 2^17 (2.8), 3.5 at 2^14
+// (single-pass block: 4.3).  Default: 2^15 only.  DSC_CLUSTER_LGS=14,15,16,17 selects others (tests do), DSC_NO_CLUSTER=1 none.
+inline bool cluster_wanted(const int lg_n) {
+    static const unsigned mask = [] {
+        const char *off = getenv("DSC_NO_CLUSTER");
+        if (off != nullptr && *off != '\0' && *off != '0') return 0u;
+        const char *e = getenv("DSC_CLUSTER_LGS");
+        if (e == nullptr || *e == '\0') return 1u << 15;
+        unsigned m = 0;
+        for (const char *c = e; *c;) {
+            const int v = atoi(c);
+            if (v > 0 && v < 32) m |= 1u << v;
+            while (*c && *c != ',') ++c;
+            if (*c == ',') ++c;
+        }
+        return m;
+    }();
+    return (mask >> lg_n) & 1u;
+}
+
+// One line per thread-block cluster (fft_cluster.cuh): dense complex lines of 2^14 .. 2^17 points, one pass over HBM.
+// Returns 1 when the shape / device is not covered, 0 on success, < 0 on error.
+template <typename T, bool FWD>
+int cluster_launch(const dsc_cuda_plan *p, const void *x, long long x_row_stride, void *dst, long long dst_row_stride,
+                   long long rows, bool scale, void *stream) {
+    using V = cx<T>;
+    if (p->col_lg_n2 == 0 || !cluster_wanted(p->lg_n)) return 1;
+    ClusterEntry *ce = cluster_entry<T, FWD>(p->col_lg_n1, p->col_lg_n2);
+    if (ce == nullptr || ce->state < 0) return 1;
+    const long long n = p->n, n1 = 1LL << p->col_lg_n1, n2 = 1LL << p->col_lg_n2;
+    if ((uintptr_t)x % 16 != 0 || (uintptr_t)dst % 16 != 0 || ((size_t)x_row_stride * sizeof(V)) % 16 != 0 ||
+        ((size_t)dst_row_stride * sizeof(V)) % 16 != 0 || x_row_stride < n || dst_row_stride < n || rows <= 0 ||
+        rows * ce->blocks >= 0x7fffffffLL)
+        return 1;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)ce->blocks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(rows * ce->blocks), 1, 1);
+    cfg.blockDim = dim3(CLUSTER_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)ce->smem;
+    cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (ce->state == 0) {
+        cudaError_t err = cudaFuncSetAttribute((const void *)ce->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce->smem);
+        if (err == cudaSuccess && ce->blocks > 8)
+            err = cudaFuncSetAttribute((const void *)ce->fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int clusters = 0;
+        if (err == cudaSuccess) err = cudaOccupancyMaxActiveClusters(&clusters, (const void *)ce->fn, &cfg);
+        if (err != cudaSuccess || clusters < 1) { cudaGetLastError(); ce->state = -1; return 1; }
+        ce->state = 1;
+    }
+    CUtensorMap map_x, map_out;
+    if (!encode_3d(&map_x, x, sizeof(V), (unsigned long long)n2, (unsigned long long)n1, (unsigned long long)rows,
+                   (unsigned long long)n2, (unsigned long long)x_row_stride, (unsigned)ce->l, (unsigned)ce->box_a) ||
+        !encode_3d(&map_out, dst, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, (unsigned long long)rows,
+                   (unsigned long long)n1, (unsigned long long)dst_row_stride, (unsigned)ce->lp, (unsigned)ce->box_b))
+        return 1;
+    ClusterArgs a{};
+    for (int i = 0; i < DSC_CUDA_MAX_STAGES; ++i) { a.tw_a[i] = p->col_tw1[i]; a.tw_b[i] = p->col_tw2[i]; }
+    a.tw_lo = p->col_lo; a.tw_hi = p->col_hi;
+    a.four_shift = p->col_shift; a.four_mask = (1 << p->col_shift) - 1;
+    a.do_scale = scale; a.scale = 1.0 / (double)n;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, ce->fn, map_x, map_out, a);
+    if (le != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "fft_cluster: %s", cudaGetErrorString(le));
+    return check_launch("fft_cluster");
+}
 #endif
 
 // The two passes of the four-step decomposition n = n1*n2 of `rows` lines:
@@ -395,7 +467,13 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
 
 #if !defined(DSC_EMUL)
     {
-        // dense complex rows: the TMA-fed launch (bulk tensor copies into shared memory, fft_tma.cuh)
+        // dense complex rows up to 2^17 points: one line per thread-block cluster, the transpose through distributed
+        // shared memory (fft_cluster.cuh); beyond that the TMA-fed two-pass launch (fft_tma.cuh)
+        if (first.in_kind == IN_COMPLEX && first.in_limit >= n && first.seg_shift == 0 && first.gi.lstride == 1 &&
+            first.gi.estride == n2 && first.ring_in == 0) {
+            const int rcc = cluster_launch<T, FWD>(p, first.x, first.gi.ostride, dst, dst_row_stride, rows, scale, stream);
+            if (rcc <= 0) return rcc;
+        }
         const int rc = four_step_tma_launch<T, FWD>(p, first, rows, work, work_bytes, dst, dst_row_stride, scale, stream, keep_out);
         if (rc <= 0) return rc;
     }
@@ -637,6 +715,13 @@ int run_fft(const dsc_cuda_plan *p, const void *x, bool x_real, void *out,
         a.do_scale = !FWD; a.scale = 1.0 / (double)n;
         // dense last-axis lines in whole blocks take the bandwidth path
         KernelEntry *fast = get_table<T, FWD, MODE_FAST, false>();
+#if !defined(DSC_EMUL)
+        if (inner == 1 && !x_real && x_n == n && p->col_lg_n2 != 0) {
+            // 2^14-point lines fill a whole SM's shared memory in one block; split over a cluster of two they overlap
+            const int rcc = cluster_launch<T, FWD>(p, x, n, out, n, outer, !FWD, stream);
+            if (rcc <= 0) return rcc;
+        }
+#endif
         if (inner == 1 && !x_real && x_n == n && a.lines % fast[p->lg_n].lpb == 0)
             return launch_lines(fast, p->lg_n, a, stream);
         // long columns: both passes of the plan's column decomposition in one launch (whole 64-512-byte
@@ -711,17 +796,19 @@ int run_rfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, 
 
 template <typename T>
 int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, int x_n, long long inner,
-              void *work, size_t work_bytes, void *stream) {
+              void *work, size_t work_bytes, void *stream, int keep = 0) {
     using V = cx<T>;
     const long long n = p->n;
     const long long take = x_n < n + 1 ? x_n : n + 1;
+    if (keep && (p->lg_n2 != 0 || inner != 1)) return fail(DSC_CUDA_EUNSUPPORTED, "fused crop: single-pass orders along the last axis only");
     if (p->lg_n2 == 0) {
         FftArgs a{};
         a.x = x; a.out = out;
         a.lines = outer * inner;
         a.inner = inner;
         a.gi = LineGeom{(long long)x_n * inner, 1, inner};
-        a.go = LineGeom{2 * n * inner, 1, 2 * inner};            // REAL elements
+        a.go = LineGeom{(keep ? (long long)keep : 2 * n) * inner, 1, 2 * inner};            // REAL elements
+        a.out_take = keep;
         a.go_pstride = inner;
         a.in_limit = take * inner;
         set_stage_tables<T>(a, p->tw1);
@@ -729,7 +816,7 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
         a.strided = inner > 1;
         a.do_scale = 1; a.scale = 1.0 / (double)n;               // 2/(2n), dsc_fft.h:232
         KernelEntry *fast = get_table<T, false, MODE_C2R_FAST, false>();
-        if (inner == 1 && x_n == n + 1 && p->lg_n >= real_fast_min_lg<T>() && a.lines % fast[p->lg_n].lpb == 0 &&
+        if (!keep && inner == 1 && x_n == n + 1 && p->lg_n >= real_fast_min_lg<T>() && a.lines % fast[p->lg_n].lpb == 0 &&
             (uintptr_t)out % (2 * sizeof(T)) == 0)
             return launch_lines(fast, p->lg_n, a, stream);
         return launch_lines(get_table<T, false, MODE_C2R, false>(), p->lg_n, a, stream, sizeof(T));
@@ -767,10 +854,11 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
 
 template <typename T>
 int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void *out, long long outer, int x_n,
-               void *work, size_t work_bytes, void *stream) {
+               void *work, size_t work_bytes, void *stream, int keep = 0) {
     using V = cx<T>;
     const long long n = p->n;
     const long long take = x_n < 2 * n ? x_n : 2 * n;
+    if (keep && p->lg_n2 != 0) return fail(DSC_CUDA_EUNSUPPORTED, "fused crop: single-pass orders only");
     if (p->lg_n2 == 0) {
         FftArgs a{};
         a.x = x; a.out = out;
@@ -778,7 +866,8 @@ int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void
         a.inner = 1;
         a.gi = LineGeom{(long long)x_n, 1, 2};                   // REAL elements
         a.gi_pstride = 1;
-        a.go = LineGeom{2 * n, 1, 2};                            // REAL elements
+        a.go = LineGeom{keep ? (long long)keep : 2 * n, 1, 2};   // REAL elements
+        a.out_take = keep;
         a.go_pstride = 1;
         a.in_limit = take;
         set_stage_tables<T>(a, p->tw1);
@@ -1012,6 +1101,24 @@ int dsc_cuda_irfft(const dsc_cuda_plan *plan, const void *x, void *out,
                                        : run_irfft<double>(plan, x, out, outer, x_n, inner, work, work_bytes, stream);
 }
 
+int dsc_cuda_irfft_keep(const dsc_cuda_plan *plan, const void *x, void *out, int64_t outer, int x_n, int keep,
+                        void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || plan->fft_type != DSC_CUDA_FFT_REAL || !x || !out || x_n < 1 || outer < 0 || keep < 1 || keep > 2 * plan->n)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_irfft_keep: bad argument");
+    if (keep == 2 * plan->n) keep = 0;
+    return plan->dtype == DSC_CUDA_F32 ? run_irfft<float>(plan, x, out, outer, x_n, 1, work, work_bytes, stream, keep)
+                                       : run_irfft<double>(plan, x, out, outer, x_n, 1, work, work_bytes, stream, keep);
+}
+
+int dsc_cuda_filter_keep(const dsc_cuda_plan *plan, const void *x, const void *spectrum, void *out,
+                         int64_t outer, int x_n, int keep, void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || plan->fft_type != DSC_CUDA_FFT_REAL || !x || !spectrum || !out || x_n < 1 || outer < 0 || keep < 1 || keep > 2 * plan->n)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_filter_keep: bad argument");
+    if (keep == 2 * plan->n) keep = 0;
+    return plan->dtype == DSC_CUDA_F32 ? run_filter<float>(plan, x, spectrum, out, outer, x_n, work, work_bytes, stream, keep)
+                                       : run_filter<double>(plan, x, spectrum, out, outer, x_n, work, work_bytes, stream, keep);
+}
+
 size_t dsc_cuda_filter_work_bytes(const dsc_cuda_plan *plan, int64_t lines) {
     if (!plan_ok(plan) || plan->lg_n2 == 0 || lines <= 0) return 0;
     // packed spectrum rows of the lines in flight (about as many as keep the GPU busy) + four-step work
@@ -1131,6 +1238,167 @@ int dsc_cuda_transpose_cast(const void *in, int in_dtype, void *out, int64_t row
         default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_cast: dtype %d", in_dtype);
     }
     return check_launch("transpose_cast_pad");
+}
+
+}  // extern "C"
+
+namespace {
+template <typename Tin>
+int cast_from(const void *x, void *out, int out_dtype, long long n, void *stream) {
+    const int blocks = pointwise_blocks(n);
+    switch (out_dtype) {
+    case DSC_CUDA_F32: { auto k = pointwise_cast<Tin, float>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Tin *)x, (float *)out, n); break; }
+    case DSC_CUDA_F64: { auto k = pointwise_cast<Tin, double>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Tin *)x, (double *)out, n); break; }
+    case DSC_CUDA_C32: { auto k = pointwise_cast<Tin, float2>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Tin *)x, (float2 *)out, n); break; }
+    case DSC_CUDA_C64: { auto k = pointwise_cast<Tin, double2>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Tin *)x, (double2 *)out, n); break; }
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_cast: unknown dtype %d", out_dtype);
+    }
+    return check_launch("pointwise_cast");
+}
+
+template <typename Ta, typename Tb, typename V>
+int mixed_by_op(int op, const void *a, const void *b, void *out, long long rows, long long cols, int b_mode, void *stream) {
+    const int blocks = pointwise_blocks(rows * cols);
+    switch (op) {
+    case DSC_CUDA_OP_ADD: { auto k = pointwise_binary_mixed<Ta, Tb, V, 0>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Ta *)a, (const Tb *)b, (V *)out, rows, cols, b_mode); break; }
+    case DSC_CUDA_OP_SUB: { auto k = pointwise_binary_mixed<Ta, Tb, V, 1>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Ta *)a, (const Tb *)b, (V *)out, rows, cols, b_mode); break; }
+    case DSC_CUDA_OP_MUL: { auto k = pointwise_binary_mixed<Ta, Tb, V, 2>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Ta *)a, (const Tb *)b, (V *)out, rows, cols, b_mode); break; }
+    case DSC_CUDA_OP_DIV: { auto k = pointwise_binary_mixed<Ta, Tb, V, 3>; DSC_LAUNCH(k, blocks, 256, 0, stream, (const Ta *)a, (const Tb *)b, (V *)out, rows, cols, b_mode); break; }
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary_mixed: unknown op %d", op);
+    }
+    return check_launch("pointwise binary (mixed dtypes)");
+}
+// the reference's two-operand conversion table, dsc_dtype.h:73-78, as types
+template <typename Ta, typename Tb> struct Promote;
+template <> struct Promote<float, float> { using type = float; };
+template <> struct Promote<float, double> { using type = double; };
+template <> struct Promote<float, float2> { using type = float2; };
+template <> struct Promote<float, double2> { using type = double2; };
+template <> struct Promote<double, float> { using type = double; };
+template <> struct Promote<double, double> { using type = double; };
+template <> struct Promote<double, float2> { using type = float2; };
+template <> struct Promote<double, double2> { using type = double2; };
+template <> struct Promote<float2, float> { using type = float2; };
+template <> struct Promote<float2, double> { using type = float2; };
+template <> struct Promote<float2, float2> { using type = float2; };
+template <> struct Promote<float2, double2> { using type = double2; };
+template <> struct Promote<double2, float> { using type = double2; };
+template <> struct Promote<double2, double> { using type = double2; };
+template <> struct Promote<double2, float2> { using type = double2; };
+template <> struct Promote<double2, double2> { using type = double2; };
+
+template <typename Ta>
+int mixed_by_b(int op, const void *a, const void *b, int b_dtype, void *out, long long rows, long long cols, int b_mode, void *stream) {
+    switch (b_dtype) {
+    case DSC_CUDA_F32: return mixed_by_op<Ta, float, typename Promote<Ta, float>::type>(op, a, b, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_F64: return mixed_by_op<Ta, double, typename Promote<Ta, double>::type>(op, a, b, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_C32: return mixed_by_op<Ta, float2, typename Promote<Ta, float2>::type>(op, a, b, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_C64: return mixed_by_op<Ta, double2, typename Promote<Ta, double2>::type>(op, a, b, out, rows, cols, b_mode, stream);
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary_mixed: unknown dtype %d", b_dtype);
+    }
+}
+
+template <typename U>
+int gather_typed(const void *in, void *out, const Index4 &g, long long total, void *stream) {
+    auto k = gather_strided<U>;
+    DSC_LAUNCH(k, pointwise_blocks(total), 256, 0, stream, (const U *)in, (U *)out, g, total);
+    return check_launch("gather_strided");
+}
+template <typename U>
+int scatter_typed(void *dst, const void *src, const Index4 &g, long long total, long long src_count, void *stream) {
+    auto k = scatter_strided<U>;
+    DSC_LAUNCH(k, pointwise_blocks(total), 256, 0, stream, (U *)dst, (const U *)src, g, total, src_count);
+    return check_launch("scatter_strided");
+}
+bool make_index4(Index4 &g, const int shape[4], const int64_t stride[4], int64_t base, long long &total) {
+    total = 1;
+    for (int d = 0; d < 4; ++d) {
+        if (shape[d] < 1) return false;
+        g.shape[d] = shape[d];
+        g.stride[d] = (long long)stride[d];
+        total *= shape[d];
+    }
+    g.base = (long long)base;
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+int dsc_cuda_cast(const void *x, int x_dtype, void *out, int out_dtype, int64_t count, void *stream) {
+    if (!x || !out || count < 0) return fail(DSC_CUDA_EINVAL, "dsc_cuda_cast: bad argument");
+    if (count == 0) return 0;
+    switch (x_dtype) {
+    case DSC_CUDA_F32: return cast_from<float>(x, out, out_dtype, (long long)count, stream);
+    case DSC_CUDA_F64: return cast_from<double>(x, out, out_dtype, (long long)count, stream);
+    case DSC_CUDA_C32: return cast_from<float2>(x, out, out_dtype, (long long)count, stream);
+    case DSC_CUDA_C64: return cast_from<double2>(x, out, out_dtype, (long long)count, stream);
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_cast: unknown dtype %d", x_dtype);
+    }
+}
+
+int dsc_cuda_binary_mixed(int op, const void *a, int a_dtype, const void *b, int b_dtype, void *out,
+                          int64_t rows, int64_t cols, int b_mode, void *stream) {
+    if (!a || !b || !out || rows < 0 || cols < 0 || b_mode < 0 || b_mode > 2) return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary_mixed: bad argument");
+    if (rows * cols == 0) return 0;
+    switch (a_dtype) {
+    case DSC_CUDA_F32: return mixed_by_b<float>(op, a, b, b_dtype, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_F64: return mixed_by_b<double>(op, a, b, b_dtype, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_C32: return mixed_by_b<float2>(op, a, b, b_dtype, out, rows, cols, b_mode, stream);
+    case DSC_CUDA_C64: return mixed_by_b<double2>(op, a, b, b_dtype, out, rows, cols, b_mode, stream);
+    default: return fail(DSC_CUDA_EINVAL, "dsc_cuda_binary_mixed: unknown dtype %d", a_dtype);
+    }
+}
+
+int dsc_cuda_fftfreq(void *out, int dtype, int n, double d, int rfft, void *stream) {
+    if (!out || n < 1) return fail(DSC_CUDA_EINVAL, "dsc_cuda_fftfreq: bad argument");
+    const int odd = n & 1, half = odd ? (n - 1) >> 1 : n >> 1;
+    const int count = rfft ? half + 1 : n;
+    const int neg_from = rfft ? count : half + odd;
+    const int blocks = (count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184;
+    if (dtype == DSC_CUDA_F32) {
+        const float factor = 1 / ((float)n * (float)d);
+        DSC_LAUNCH(fill_fftfreq<float>, blocks, 256, 0, stream, (float *)out, count, neg_from, factor);
+    } else if (dtype == DSC_CUDA_F64) {
+        const double factor = 1 / ((double)n * d);
+        DSC_LAUNCH(fill_fftfreq<double>, blocks, 256, 0, stream, (double *)out, count, neg_from, factor);
+    } else return fail(DSC_CUDA_EINVAL, "dsc_cuda_fftfreq: dtype must be real");
+    return check_launch("fill_fftfreq");
+}
+
+int dsc_cuda_gather(const void *in, void *out, int elem_bytes, const int shape[4], const int64_t stride[4], int64_t base, void *stream) {
+    Index4 g;
+    long long total;
+    if (!in || !out || !shape || !stride || !make_index4(g, shape, stride, base, total)) return fail(DSC_CUDA_EINVAL, "dsc_cuda_gather: bad argument");
+    if (elem_bytes == 4) return gather_typed<float>(in, out, g, total, stream);
+    if (elem_bytes == 8) return gather_typed<float2>(in, out, g, total, stream);
+    if (elem_bytes == 16) return gather_typed<double2>(in, out, g, total, stream);
+    return fail(DSC_CUDA_EINVAL, "dsc_cuda_gather: element size %d", elem_bytes);
+}
+
+int dsc_cuda_scatter(void *dst, const void *src, int elem_bytes, const int shape[4], const int64_t stride[4], int64_t base,
+                     int64_t src_count, void *stream) {
+    Index4 g;
+    long long total;
+    if (!dst || !src || !shape || !stride || src_count < 1 || !make_index4(g, shape, stride, base, total))
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_scatter: bad argument");
+    if (elem_bytes == 4) return scatter_typed<float>(dst, src, g, total, (long long)src_count, stream);
+    if (elem_bytes == 8) return scatter_typed<float2>(dst, src, g, total, (long long)src_count, stream);
+    if (elem_bytes == 16) return scatter_typed<double2>(dst, src, g, total, (long long)src_count, stream);
+    return fail(DSC_CUDA_EINVAL, "dsc_cuda_scatter: element size %d", elem_bytes);
+}
+
+int dsc_cuda_transpose_batched(const void *in, void *out, int64_t batches, int64_t rows, int64_t cols, int elem_bytes, void *stream) {
+    if (!in || !out || batches <= 0 || rows <= 0 || cols <= 0 || rows > 0x7fffffff || cols > 0x7fffffff)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_batched: bad argument");
+    const long long per = ((rows + 31) / 32) * ((cols + 31) / 32);
+    if (per * batches > 0x7fffffffLL) return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_batched: too many tiles");
+    const unsigned grid = (unsigned)(per * batches);
+    if (elem_bytes == 4) { auto k = transpose_batched<float>; DSC_LAUNCH(k, grid, 256, 0, stream, (const float *)in, (float *)out, (int)rows, (int)cols, per); }
+    else if (elem_bytes == 8) { auto k = transpose_batched<float2>; DSC_LAUNCH(k, grid, 256, 0, stream, (const float2 *)in, (float2 *)out, (int)rows, (int)cols, per); }
+    else if (elem_bytes == 16) { auto k = transpose_batched<double2>; DSC_LAUNCH(k, grid, 256, 0, stream, (const double2 *)in, (double2 *)out, (int)rows, (int)cols, per); }
+    else return fail(DSC_CUDA_EINVAL, "dsc_cuda_transpose_batched: element size %d", elem_bytes);
+    return check_launch("transpose_batched");
 }
 
 }  // extern "C"

@@ -266,6 +266,13 @@ extern dsc_tensor *dsc_rfftfreq(dsc_ctx *ctx, int n, f64 d = 1., dsc_dtype dtype
 // one launch sequence, the spectrum never leaves the GPU.  Output has 2*order samples per line.
 extern dsc_tensor *dsc_fft_filter(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const dsc_tensor *DSC_RESTRICT B,
                                   dsc_tensor *DSC_RESTRICT out = nullptr, int n = -1, int axis = -1) noexcept;
+// irfft / dsc_fft_filter along the last axis keeping only the first `keep` samples of every line: the README's
+// `irfft(...)[:output_length]` (README.md:130-133, i.e. dsc_irfft followed by dsc_tensor_get_slice, dsc.cpp:950-1007)
+// with the crop fused into the inverse kernel's store -- cropped samples are neither written nor downloaded.
+extern dsc_tensor *dsc_irfft_keep(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, dsc_tensor *DSC_RESTRICT out,
+                                  int n, int axis, int keep) noexcept;
+extern dsc_tensor *dsc_fft_filter_keep(dsc_ctx *ctx, const dsc_tensor *DSC_RESTRICT x, const dsc_tensor *DSC_RESTRICT B,
+                                       dsc_tensor *DSC_RESTRICT out, int n, int axis, int keep) noexcept;
 // Residency policy of FFT results (see DESIGN.md "Host-visible data vs device residency").
 //   0 (default): every call uploads its inputs and downloads its outputs -- always coherent with host writes;
 //   1: outputs stay valid on the device and are reused as inputs without upload (host writes through

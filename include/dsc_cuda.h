@@ -137,6 +137,15 @@ size_t dsc_cuda_filter_work_bytes(const dsc_cuda_plan *plan, int64_t lines);
 int dsc_cuda_filter(const dsc_cuda_plan *plan, const void *x, const void *spectrum, void *out,
                     int64_t outer, int x_n, void *work, size_t work_bytes, void *stream);
 
+/* irfft / fused filter along the last axis storing only the first `keep` (<= 2n) real samples of every line; out is
+ * (outer, keep).  The crop of README.md:130-133 (`y[:output_length]`, dsc_tensor_get_slice dsc.cpp:950-1007) fused into
+ * the inverse kernel's store: the cropped samples are never written.  Orders of one shared-memory pass only
+ * (DSC_CUDA_EUNSUPPORTED otherwise: the caller transforms in full and crops with dsc_cuda_gather). */
+int dsc_cuda_irfft_keep(const dsc_cuda_plan *plan, const void *x, void *out, int64_t outer, int x_n, int keep,
+                        void *work, size_t work_bytes, void *stream);
+int dsc_cuda_filter_keep(const dsc_cuda_plan *plan, const void *x, const void *spectrum, void *out,
+                         int64_t outer, int x_n, int keep, void *work, size_t work_bytes, void *stream);
+
 /* out = a * b elementwise on complex rows; b has `cols` elements (b_rows == 0, broadcast)
  * or rows*cols (b_rows != 0). */
 int dsc_cuda_cmul(const void *a, const void *b, void *out, int dtype,
@@ -153,6 +162,33 @@ enum { DSC_CUDA_OP_ADD = 0, DSC_CUDA_OP_SUB = 1, DSC_CUDA_OP_MUL = 2, DSC_CUDA_O
 int dsc_cuda_unary(int op, const void *x, int x_dtype, void *out, int64_t count, void *stream);
 int dsc_cuda_binary(int op, const void *a, const void *b, void *out, int dtype,
                     int64_t rows, int64_t cols, int b_mode, void *stream);
+
+/* Cast between any two of F32 / F64 / C32 / C64 (cast_op, dsc/include/dsc_ops.h:12-44: real -> complex sets imag = 0,
+ * complex -> real keeps the real part).  dsc_cast, dsc/src/dsc.cpp:587-597. */
+int dsc_cuda_cast(const void *x, int x_dtype, void *out, int out_dtype, int64_t count, void *stream);
+
+/* out = a OP b with operands of DIFFERENT dtypes: both are promoted to out_dtype = table[a_dtype][b_dtype]
+ * (dsc_dtype.h:73-78) in registers, where the reference casts them through scratch first (dsc.cpp:44-69).
+ * rows / cols / b_mode as in dsc_cuda_binary. */
+int dsc_cuda_binary_mixed(int op, const void *a, int a_dtype, const void *b, int b_dtype, void *out,
+                          int64_t rows, int64_t cols, int b_mode, void *stream);
+
+/* fftfreq (rfft == 0): out[i] = i / (n d) for i < n - n/2, (i - n) / (n d) above, n values;
+ * rfftfreq (rfft != 0): out[i] = i / (n d), n/2 + 1 values.  dtype F32 / F64; the factor 1 / (n d) is formed and
+ * applied in that precision like dsc_internal_fftfreq, dsc/src/dsc.cpp:2262-2339. */
+int dsc_cuda_fftfreq(void *out, int dtype, int n, double d, int rfft, void *stream);
+
+/* Strided gather / scatter over a right-aligned 4-D index space -- the device side of dsc_transpose (dsc.cpp:764-827),
+ * dsc_tensor_get_slice (:950-1007) and dsc_tensor_set_slice (:1108-1169).  shape[4] are the extents of the dense side
+ * (row-major), stride[4] / base the element strides / offset of the strided side; elem_bytes in {4, 8, 16}.
+ *   gather : out[dense i] = in[base + sum idx_d stride_d]
+ *   scatter: dst[base + sum idx_d stride_d] = src[dense i mod src_count]  (the source is recycled when shorter) */
+int dsc_cuda_gather(const void *in, void *out, int elem_bytes, const int shape[4], const int64_t stride[4], int64_t base, void *stream);
+int dsc_cuda_scatter(void *dst, const void *src, int elem_bytes, const int shape[4], const int64_t stride[4], int64_t base,
+                     int64_t src_count, void *stream);
+
+/* out[b][c][r] = in[b][r][c]: tiled transpose of the last two dims of `batches` matrices, elem_bytes in {4, 8, 16}. */
+int dsc_cuda_transpose_batched(const void *in, void *out, int64_t batches, int64_t rows, int64_t cols, int elem_bytes, void *stream);
 
 /* ---- building blocks of the multi-GPU four-step (one transform sharded over P GPUs) ----------
  * out[k] = exp(-2 pi i (k * mult mod denom) / denom), k < count: the two sqrt(M)-sized tables

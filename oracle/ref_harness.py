@@ -108,6 +108,13 @@ class RefLib:
             getattr(lib, name).restype = _TP
             getattr(lib, name).argtypes = [C.c_void_p, _TP]
         lib.dsc_tensor_get_slice.restype = _TP
+        lib.dsc_tensor_set_slice.restype = None
+        lib.dsc_cast.restype = _TP
+        lib.dsc_cast.argtypes = [C.c_void_p, _TP, C.c_uint8]
+        lib.dsc_transpose.restype = _TP
+        for name in ("dsc_fftfreq", "dsc_rfftfreq"):
+            getattr(lib, name).restype = _TP
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint8]
         lib.dsc_traces_record.argtypes = [C.c_void_p, C.c_bool]
         lib.dsc_dump_traces.argtypes = [C.c_void_p, C.c_char_p]
         lib.dsc_clear_traces.argtypes = [C.c_void_p]
@@ -205,6 +212,65 @@ class RefLib:
         res = self.get(to)
         self.free(to)
         self.free(tx)
+        return res
+
+    @staticmethod
+    def _slice_args(slices):
+        """python slices / ints -> dsc_slice structs (the wrappers' single-index convention for ints)."""
+        out = []
+        for it in slices:
+            if isinstance(it, slice):
+                out.append(_Slice(VALUE_NONE if it.start is None else it.start, VALUE_NONE if it.stop is None else it.stop,
+                                  VALUE_NONE if it.step is None else it.step))
+            else:
+                out.append(_Slice(int(it), int(it), int(it)))
+        return out
+
+    def get_slice(self, x, slices):
+        """dsc_tensor_get_slice (dsc.cpp:950-1007) with NumPy-style slices."""
+        tx = self.put(x)
+        args = self._slice_args(slices)
+        to = self.lib.dsc_tensor_get_slice(self.ctx, tx, C.c_int(len(args)), *args)
+        res = self.get(to)
+        self.free(to)
+        self.free(tx)
+        return res
+
+    def set_slice(self, xa, xb, slices):
+        """dsc_tensor_set_slice (dsc.cpp:1108-1169): returns xa after xa[slices] = xb."""
+        ta, tb = self.put(xa), self.put(xb)
+        args = self._slice_args(slices)
+        self.lib.dsc_tensor_set_slice(self.ctx, ta, tb, C.c_int(len(args)), *args)
+        res = self.get(ta)
+        self.free(tb)
+        self.free(ta)
+        return res
+
+    def cast(self, x, np_dtype):
+        """dsc_cast (dsc.cpp:587-597)."""
+        tx = self.put(x)
+        to = self.lib.dsc_cast(self.ctx, tx, _NP2DSC[np.dtype(np_dtype)])
+        res = self.get(to)
+        if C.addressof(to.contents) != C.addressof(tx.contents):
+            self.free(to)
+        self.free(tx)
+        return res
+
+    def transpose(self, x, axes=()):
+        """dsc_transpose (dsc.cpp:764-827); no axes = reversed dims."""
+        tx = self.put(x)
+        to = self.lib.dsc_transpose(self.ctx, tx, C.c_int(len(axes)), *[C.c_int(int(a)) for a in axes])
+        res = self.get(to)
+        self.free(to)
+        self.free(tx)
+        return res
+
+    def fftfreq(self, n, d=1.0, np_dtype=np.float64, rfft=False):
+        """dsc_fftfreq / dsc_rfftfreq (dsc.cpp:2262-2339)."""
+        f = self.lib.dsc_rfftfreq if rfft else self.lib.dsc_fftfreq
+        to = f(self.ctx, int(n), float(d), _NP2DSC[np.dtype(np_dtype)])
+        res = self.get(to)
+        self.free(to)
         return res
 
     # -- misc ------------------------------------------------------------------------

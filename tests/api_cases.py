@@ -246,6 +246,84 @@ def check_device_pointwise(dsc):
         dsc.set_residency(0)
 
 
+def _py_slices(enc):
+    return tuple(slice(*e) if isinstance(e, list) else int(e) for e in enc)
+
+
+def check_device_ops(dsc):
+    """SURVEY.md 8(f) ranks 1, 3 and 4 against what the unmodified reference returned (tests/golden/ops_golden.npz):
+    dsc_cast, mixed-dtype add/sub/mul/div, dsc_transpose, dsc_fftfreq / dsc_rfftfreq, dsc_tensor_get_slice /
+    set_slice -- through the host loops (strict mode) and through the device kernels (operands device-resident;
+    in mode 2 results stay on the device until read)."""
+    from tests.util import load_ops_golden
+    gold = list(load_ops_golden())
+    assert len(gold) >= 280
+    fn = {"add": dsc.add, "sub": dsc.sub, "mul": dsc.mul, "div": dsc.true_div}
+    try:
+        for mode in (0, 1, 2):
+            dsc.set_residency(mode)
+            for meta, arrs in gold:
+                op = meta["op"]
+                want = arrs["y"]
+                if op in ("fftfreq", "rfftfreq"):
+                    got = getattr(dsc, op)(meta["n"], meta["d"], np.dtype(meta["dtype"]))
+                    g = got.numpy()
+                    assert g.shape == want.shape and g.dtype == want.dtype, (meta, mode)
+                    assert np.array_equal(g, want), (meta, mode, np.max(np.abs(g - want)))
+                    continue
+                x = dsc.from_numpy(arrs["x"])
+                dsc.prefetch(x)                              # device-resident in modes 1 and 2, a no-op in strict mode
+                exact = True
+                if op == "cast":
+                    got = x.cast(np.dtype(meta["to"]))
+                elif op.startswith("binary:"):
+                    name = op.split(":")[1]
+                    got = fn[name](x, dsc.from_numpy(arrs["b"]))
+                    exact = name in ("add", "sub")
+                elif op == "transpose":
+                    got = dsc.transpose(x, meta["axes"] or None)
+                elif op == "get_slice":
+                    got = x[_py_slices(meta["slices"])]
+                elif op == "set_slice":
+                    if mode == 2:
+                        # make the device copy the only current one, as after a transform in lazy mode
+                        x = dsc.add(x, dsc.from_numpy(np.zeros(1, dtype=arrs["x"].dtype)))
+                    x[_py_slices(meta["slices"])] = dsc.from_numpy(arrs["b"])
+                    got = x
+                else:
+                    raise AssertionError(op)
+                g = got.numpy()
+                assert g.shape == want.shape and g.dtype == want.dtype, (meta, mode, g.shape, want.shape)
+                if exact:
+                    assert np.array_equal(g, want), (meta, mode)
+                else:
+                    assert rel_l2(g, want) < TOL[want.dtype] * 1e-1, (meta, mode, rel_l2(g, want))
+            # spectrum post-processing chained behind a transform, nothing returning to the host in between:
+            # magnitude of the upper half of a transposed spectrum, cast to double
+            z = randn(np.random.default_rng(6), (8, 128), "complex64")
+            Z = dsc.fft(z)
+            half = dsc.transpose(Z)[64:, :]
+            mag = dsc.abs(half).cast(np.float64)
+            ref = np.abs(port.fft(z).T[64:, :]).astype(np.float64)
+            assert mag.numpy().dtype == np.float64 and rel_l2(mag.numpy(), ref) < 1e-5
+            del Z, half, mag
+            # irfft / fused filter with the crop fused into the store (README.md:130-133), single-pass and two-pass orders
+            for n_fft, rows in ((2048, 5), (1 << 16, 2)):
+                sig = randn(np.random.default_rng(7), (rows, n_fft // 2 - 24), "float32")
+                taps = randn(np.random.default_rng(8), (37,), "float32")
+                keep = sig.shape[1] + 36
+                B = dsc.rfft(taps, n=n_fft)
+                y1 = dsc.irfft_keep(dsc.rfft(sig, n=n_fft) * B, keep)
+                y2 = dsc.fft_filter_keep(sig, B, keep, n=n_fft)
+                assert y1.shape == (rows, keep) and y2.shape == (rows, keep)
+                for r in range(rows):
+                    w = port.filter_fft(sig[r], taps, n_fft)[:keep]
+                    assert rel_l2(y1.numpy()[r], w) < 1e-5 and rel_l2(y2.numpy()[r], w) < 1e-5
+                del B, y1, y2
+    finally:
+        dsc.set_residency(0)
+
+
 def check_traces(dsc):
     rng = np.random.default_rng(17)
     x = dsc.from_numpy(randn(rng, (4, 64), "float32"))

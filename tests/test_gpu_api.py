@@ -25,6 +25,7 @@ def dsc():
 CASES = [api_cases.check_golden, api_cases.check_shapes_appendix_a, api_cases.check_out_param,
          api_cases.check_vs_oracle_sweep, api_cases.check_filter_pipeline, api_cases.check_plan_cache,
          api_cases.check_memory_accounting, api_cases.check_residency_modes, api_cases.check_device_pointwise,
+         api_cases.check_device_ops,
          api_cases.check_traces,
          api_cases.check_composed_paths]
 

@@ -1,0 +1,26 @@
+"""Every implementation of the lengths beyond one shared-memory pass, against the oracle on the B200:
+   default      TMA-fed two-pass launch (fft_tma.cuh), thread-block clusters for 2^15-point lines (fft_cluster.cuh)
+   clusters     one line per cluster for 2^14 .. 2^17 (2, 4, 8 and 16 blocks, distributed shared memory)
+   registers    the register-direct persistent launch (four_step_fused), no TMA, no clusters
+The selection is made through environment variables the library reads once, hence one subprocess per variant."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "two_pass_worker.py")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,env", [("default", {}), ("clusters", {"DSC_CLUSTER_LGS": "14,15,16,17"}),
+                                      ("registers", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1"})])
+def test_two_pass_paths(name, env):
+    e = dict(os.environ)
+    for k in ("DSC_NO_TMA", "DSC_NO_CLUSTER", "DSC_CLUSTER_LGS"):
+        e.pop(k, None)
+    e.update(env)
+    r = subprocess.run([sys.executable, WORKER], capture_output=True, text=True, timeout=600, env=e)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -35,6 +35,18 @@ def load_golden():
         yield i, m, arrs
 
 
+OPS_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ops_golden.npz")
+
+
+def load_ops_golden():
+    """(meta, arrays) of the cases tests/golden/make_ops_golden.py recorded from the reference: cast, mixed-dtype
+    arithmetic, transpose, fftfreq / rfftfreq, get_slice / set_slice."""
+    z = np.load(OPS_GOLDEN)
+    meta = json.loads(bytes(z["meta"]).decode())
+    for i, m in enumerate(meta):
+        yield m, {k: z[f"{k}{i}"] for k in ("x", "b", "y") if f"{k}{i}" in z.files}
+
+
 def use_library(dsc, path):
     """Point the dsc_b200 binding at another build of the same C ABI (tests only: the pthread-emulated
     build where there is no GPU, the product build on the B200).  Drops the current context first."""
