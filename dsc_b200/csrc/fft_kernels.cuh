@@ -1022,6 +1022,12 @@ struct ColumnsGeom {
     int post_twiddle;
     unsigned post_mask;
     long long col_offset;
+    // optional scattered output of the second pass (the fused compute + collective of the multi-GPU transform): the
+    // rows k of the output are cut into blocks of 2^peer_shift rows, and block q is stored at peer_out[q] (row pitch
+    // `inner`, like the dense output) -- a pointer into GPU q's receive buffer, mapped into this process (NVLink
+    // peer memory).  n_peers == 0: one dense output.
+    int n_peers, peer_shift;
+    void *peer_out[8];
 };
 
 template <typename T, int LG_N, int LG_M, int LG_E, int L, int TABLE_AT, bool FWD, bool FIRST, typename Hook>
@@ -1116,11 +1122,23 @@ DSC_DEV void column_tile(const FftArgs &a, const ColumnsGeom &g, const unsigned 
             for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], (c & 3) == 0 ? hi4[c >> 2] : cmul(hi4[c >> 2], lo3[c & 3]));
         }
         // X[k1 + n1 k2], k2 = j + c TT
-        V *__restrict__ op = (V *)a.out + (long long)o * g.out_ostride + ((long long)ch << g.lg_ic) + col0 + l;
+        if (g.n_peers) {
+            // straight into the receive buffers of the GPUs that own the rows: the exchange happens while the transform
+            // runs, one row block per peer (a warp writes L * sizeof(V) contiguous bytes per row, like the dense store)
+            const long long coff = ((long long)ch << g.lg_ic) + col0 + l;
 #pragma unroll
-        for (int c = 0; c < E; ++c) {
-            const long long k = (long long)fixed + ((long long)(j + c * TT) << LG_M);
-            __stcs(op + k * g.inner, v[c]);
+            for (int c = 0; c < E; ++c) {
+                const long long k = (long long)fixed + ((long long)(j + c * TT) << LG_M);
+                V *__restrict__ pp = (V *)g.peer_out[k >> g.peer_shift];
+                pp[(k & ((1LL << g.peer_shift) - 1)) * g.inner + coff] = v[c];
+            }
+        } else {
+            V *__restrict__ op = (V *)a.out + (long long)o * g.out_ostride + ((long long)ch << g.lg_ic) + col0 + l;
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+                const long long k = (long long)fixed + ((long long)(j + c * TT) << LG_M);
+                __stcs(op + k * g.inner, v[c]);
+            }
         }
     }
 }

@@ -600,6 +600,8 @@ struct PostTwiddle {            // optional output twiddle of the column launch 
     const void *lo, *hi;
     int shift;
     long long total, col_offset;
+    int n_peers;                // > 0: the output rows go to peer_out[row block] (ColumnsGeom::peer_out)
+    void *const *peer_out;
 };
 
 template <typename T, bool FWD>
@@ -683,6 +685,11 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
         g.col_offset = post->col_offset;
         b.tw_lo = post->lo; b.tw_hi = post->hi;
         b.four_shift = post->shift; b.four_mask = (1 << post->shift) - 1;
+        if (post->n_peers > 0) {
+            g.n_peers = post->n_peers;
+            g.peer_shift = pow2_shift(n / post->n_peers);
+            for (int q = 0; q < post->n_peers; ++q) g.peer_out[q] = post->peer_out[q];
+        }
     }
 #if defined(DSC_EMUL)
     memset(work, 0, sync_bytes);
@@ -1044,7 +1051,24 @@ int dsc_cuda_fft_columns_twiddled(const dsc_cuda_plan *plan, const void *x, void
                                   void *work, size_t work_bytes, void *stream) {
     if (!plan_ok(plan) || !x || !out || cols < 1 || !tw_lo || !tw_hi || total < 1 || (total & (total - 1)) || total > (1LL << 31))
         return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_columns_twiddled: bad argument");
-    PostTwiddle post{tw_lo, tw_hi, shift, (long long)total, (long long)col_offset};
+    PostTwiddle post{tw_lo, tw_hi, shift, (long long)total, (long long)col_offset, 0, nullptr};
+    if (plan->dtype == DSC_CUDA_F32)
+        return forward ? four_step_columns_launch<float, true>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post)
+                       : four_step_columns_launch<float, false>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post);
+    return forward ? four_step_columns_launch<double, true>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post)
+                   : four_step_columns_launch<double, false>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post);
+}
+
+int dsc_cuda_fft_columns_twiddled_p2p(const dsc_cuda_plan *plan, const void *x, int64_t cols, int forward,
+                                      int64_t col_offset, const void *tw_lo, const void *tw_hi, int shift, int64_t total,
+                                      void *const *peer_out, int n_peers, void *work, size_t work_bytes, void *stream) {
+    if (!plan_ok(plan) || !x || cols < 1 || !tw_lo || !tw_hi || total < 1 || (total & (total - 1)) || total > (1LL << 31) ||
+        !peer_out || n_peers < 1 || n_peers > 8 || (n_peers & (n_peers - 1)) || plan->n % n_peers != 0)
+        return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_columns_twiddled_p2p: bad argument");
+    for (int q = 0; q < n_peers; ++q)
+        if (peer_out[q] == nullptr) return fail(DSC_CUDA_EINVAL, "dsc_cuda_fft_columns_twiddled_p2p: null peer pointer");
+    PostTwiddle post{tw_lo, tw_hi, shift, (long long)total, (long long)col_offset, n_peers, peer_out};
+    void *out = peer_out[0];     // unused by the scattered store; only has to be non-null
     if (plan->dtype == DSC_CUDA_F32)
         return forward ? four_step_columns_launch<float, true>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post)
                        : four_step_columns_launch<float, false>(plan, x, false, out, 1, plan->n, cols, work, work_bytes, stream, &post);

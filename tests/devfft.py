@@ -149,7 +149,7 @@ class DevFFT:
                                     0, self_seg, self_ptr)
         return self.mem.download(dout) if ok else None
 
-    def fft_columns_twiddled(self, x, col_offset, total, forward=True):
+    def fft_columns_twiddled(self, x, col_offset, total, forward=True, peers=0):
         """x: [n][cols] natural-order column block; returns out[k][c] = FFT over i of column c times
         W_total^((col_offset + c) k) (conjugated when not forward), or None when the shape is not covered."""
         x = np.ascontiguousarray(x)
@@ -166,6 +166,14 @@ class DevFFT:
         dout = self.mem.empty((n, cols), x.dtype)
         nbytes = self.api.work_bytes_axis(plan, 1, cols)
         w = self.mem.alloc(nbytes) if nbytes else None
+        if peers:
+            # the fused-exchange variant: row block q goes to its own buffer (here: `peers` separate local buffers
+            # standing in for the peers' receive buffers); reassembled for the comparison
+            bufs = [self.mem.empty((n // peers, cols), x.dtype) for _ in range(peers)]
+            ok = self.api.fft_columns_twiddled_p2p(plan, self.mem.ptr(dx), cols, forward, col_offset, self.mem.ptr(lo),
+                                                   self.mem.ptr(hi), shift, total, [self.mem.ptr(b) for b in bufs],
+                                                   self.mem.ptr(w) if nbytes else 0, nbytes)
+            return np.concatenate([self.mem.download(b) for b in bufs], axis=0) if ok else None
         ok = self.api.fft_columns_twiddled(plan, self.mem.ptr(dx), self.mem.ptr(dout), cols, forward, col_offset,
                                            self.mem.ptr(lo), self.mem.ptr(hi), shift, total,
                                            self.mem.ptr(w) if nbytes else 0, nbytes)

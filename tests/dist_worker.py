@@ -34,13 +34,17 @@ def main():
     out_nat = f.forward_natural(f.scatter_input_natural(torch.from_numpy(x)))
     nat_err = float(torch.linalg.norm(out_nat - out) / torch.linalg.norm(out))
     assert nat_err < 2e-6, nat_err
+    mode = f.last_mode
     back = f.gather_output(f.forward(f.scatter_input(torch.from_numpy(X)), inverse=True)).cpu().numpy()
+    # the inverse through the natural-order entry too (on GPUs: the fused exchange, conjugate twiddles)
+    back_nat = f.gather_output(f.forward_natural(f.scatter_input_natural(torch.from_numpy(X)), inverse=True)).cpu().numpy()
+    assert float(np.linalg.norm(back_nat - back) / np.linalg.norm(back)) < 2e-6
     if rank == 0:
         from oracle import port
         want = port.fft(x)                                 # DSC's CPU FFT (C restatement, pinned bit-exact)
         err = float(np.linalg.norm(X - want) / np.linalg.norm(want))
         rt = float(np.linalg.norm(back - x) / np.linalg.norm(x))
-        print(f"OK world={world} lg={lg} err={err:.3e} roundtrip={rt:.3e}", flush=True)
+        print(f"OK world={world} lg={lg} err={err:.3e} roundtrip={rt:.3e} natural-order path: {mode} (p2p unavailable: {f.p2p_error})", flush=True)
         assert err < 1e-5 and rt < 1e-5
     dist.destroy_process_group()
 

@@ -220,6 +220,9 @@ def test_columns_with_outer_twiddle(dev, dtype, lg, cols):
     wanti = np.fft.ifft(x.astype(np.complex128), axis=0) * np.exp(2j * np.pi * ((k * c) % (n * all_cols)) / (n * all_cols))
     assert rel_l2(yi, wanti.astype(dtype)) < TIGHT[dtype] * 2
     assert dev.fft_columns_twiddled(x[:1024].copy(), off, 1024 * all_cols) is None      # no column decomposition
+    # the exchange fused into the epilogue: the same numbers, row blocks scattered over per-peer buffers
+    for peers in (2, 8):
+        assert np.array_equal(dev.fft_columns_twiddled(x, off, n * all_cols, peers=peers), y)
 
 
 def test_two_pass_chunked_work_buffer():
