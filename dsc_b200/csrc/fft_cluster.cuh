@@ -186,6 +186,209 @@ fft_cluster(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same data path, pipelined: persistent clusters, three tile buffers per block, two butterfly groups, a loader and a
+// storer thread (the structure of four_step_tma), and mbarrier-signalled distributed-shared-memory stores instead of
+// whole-cluster barriers.
+//
+// A cluster walks its lines i = 0, 1, ... (line = cluster + i * clusters); line i lives in buffer i % 3 of EVERY block of
+// the cluster and is transformed by group i % 2 of every block.  Per block and line:
+//   loader : wait empty[b] -> TMA box load of the block's column block -> full[b]
+//   group  : wait full[b] -> first half (length n1) -> "my buffer may be overwritten": arrive on free[b] of every block of
+//            the cluster (count C) -> wait free[b] -> st.async each point into its owner's buffer, completing bytes on
+//            the owner's landed[b] -> wait landed[b] (64 KiB) -> second half (length n2) -> ready[b]
+//   storer : wait ready[b] -> TMA box store -> empty[b]
+// While one group waits for its peers or for bytes to land, the other group computes and the next line is already loading.
+namespace cl {
+DSC_DEV void mbar_arrive_remote(unsigned cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+DSC_DEV void mbar_wait_cluster(void *bar, unsigned parity) {
+    const unsigned a = tma::smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+DSC_DEV void store_async(unsigned addr, float2 v, unsigned mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "f"(v.x), "f"(v.y), "r"(mbar) : "memory");
+}
+DSC_DEV void store_async(unsigned addr, double2 v, unsigned mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "d"(v.x), "d"(v.y), "r"(mbar) : "memory");
+}
+DSC_DEV void sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+}  // namespace cl
+
+template <typename T, int LG_N1> struct ClusterPipeSmem {
+    using V = cx<T>;
+    static constexpr int E = 1 << tma_lg_e<T>();
+    static constexpr int L = tma_tile_points<T>() >> LG_N1;
+    alignas(1024) unsigned char buf[TMA_BUFFERS][TMA_TILE_BYTES];
+    V table[L * E];                                // W^(q TT c), [c][line]: the same for every line of the launch
+    unsigned long long full[TMA_BUFFERS];          // the block's column block has landed (TMA)
+    unsigned long long free_[TMA_BUFFERS];         // every block of the cluster has read its tile: the buffers may be overwritten
+    unsigned long long landed[TMA_BUFFERS];        // the block's rows have arrived from all blocks (st.async bytes)
+    unsigned long long ready[TMA_BUFFERS];         // the finished rows lie in the buffer
+    unsigned long long empty[TMA_BUFFERS];         // the TMA store has read the buffer
+};
+
+template <typename T, int LG_N1, int LG_N2, bool FWD>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+fft_cluster_pipe(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out, const ClusterArgs a,
+                 const unsigned lines, const unsigned clusters) {
+    using V = cx<T>;
+    constexpr int LG_E = tma_lg_e<T>(), E = 1 << LG_E;
+    constexpr int N1 = 1 << LG_N1, N2 = 1 << LG_N2;
+    constexpr int L = tma_tile_points<T>() >> LG_N1;
+    constexpr int C = N2 / L;
+    constexpr int LP = N1 / C;
+    constexpr int TT1 = N1 >> LG_E, TT2 = N2 >> LG_E;
+    static_assert(L * TT1 == TMA_GROUP_THREADS && LP * TT2 == TMA_GROUP_THREADS, "one register tile per thread in both halves");
+    using TileA = TmaTile<T, LG_N1, L, FWD, false>;
+    using TileB = TmaTile<T, LG_N2, LP, FWD, false>;
+    static_assert(TileA::STAGES == 2 && TileB::STAGES == 2, "two stages per half");
+    constexpr int SLOTS = 128 / (int)sizeof(V), LG_SLOTS = SLOTS == 16 ? 4 : 3;
+    constexpr int LG_TT2 = LG_N2 - LG_E, SH = LG_SLOTS - LG_TT2;
+    static_assert(TT2 <= SLOTS && LP >= SLOTS, "second-half swizzles assume short rows of threads and wide tiles");
+    constexpr int ES = sizeof(T) == 4 ? 1 : 2;
+
+    DSC_DYN_SMEM(smem_raw);
+    using Smem = ClusterPipeSmem<T, LG_N1>;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u));
+
+    const int tid = threadIdx.x;
+    const unsigned rank = cl::cta_rank();
+    const unsigned cid = cl::cluster_id_x();
+    const unsigned my_lines = cid < lines ? (lines - cid + clusters - 1) / clusters : 0;     // the same in every block of the cluster
+    if (tid == 0) {
+        for (int b = 0; b < TMA_BUFFERS; ++b) {
+            tma::mbar_init(&sm.full[b], 1);
+            tma::mbar_init(&sm.free_[b], C);
+            tma::mbar_init(&sm.landed[b], 1);
+            tma::mbar_init(&sm.ready[b], TMA_GROUP_THREADS);
+            tma::mbar_init(&sm.empty[b], 1);
+        }
+        tma::fence_barrier_init();
+    }
+    TmaArgs ta{};
+    ta.tw_lo = a.tw_lo; ta.tw_hi = a.tw_hi; ta.four_shift = a.four_shift; ta.four_mask = a.four_mask;
+    for (int i = tid; i < L * E; i += TMA_THREADS) {
+        const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
+        sm.table[i] = tma_twiddle<T>(ta, (rank * (unsigned)L + ll) * (unsigned)TT1 * c);
+    }
+    __syncthreads();
+    cl::sync_all();          // every block's barriers exist before anyone arrives on them remotely
+
+    if (tid >= TMA_GROUPS * TMA_GROUP_THREADS) {
+        const int warp = (tid - TMA_GROUPS * TMA_GROUP_THREADS) / 32;
+        if ((tid & 31) == 0) {
+            const unsigned long long pol_stream = tma::policy_evict_first();
+            if (warp == 0) {
+                // ---- loader
+                for (unsigned t = 0; t < my_lines; ++t) {
+                    const int b = (int)(t % TMA_BUFFERS);
+                    if (t >= TMA_BUFFERS) tma::mbar_wait(&sm.empty[b], (t / TMA_BUFFERS - 1) & 1);
+                    const unsigned line = cid + t * clusters;
+                    tma::mbar_arrive_expect_tx(&sm.full[b], TMA_TILE_BYTES);
+                    constexpr int BOX = tma_box_rows(LG_N1);
+#pragma unroll
+                    for (int r0 = 0; r0 < N1; r0 += BOX)
+                        tma::load_3d(sm.buf[b] + (size_t)r0 * L * sizeof(V), &map_x, (int)rank * L * ES, r0, (int)line, &sm.full[b], pol_stream);
+                }
+            } else {
+                // ---- storer
+                for (unsigned t = 0; t < my_lines; ++t) {
+                    const int b = (int)(t % TMA_BUFFERS);
+                    tma::mbar_wait(&sm.ready[b], (t / TMA_BUFFERS) & 1);
+                    const unsigned line = cid + t * clusters;
+                    constexpr int BOX = tma_box_rows(LG_N2);
+#pragma unroll
+                    for (int r0 = 0; r0 < N2; r0 += BOX)
+                        tma::store_3d(&map_out, (int)rank * LP * ES, r0, (int)line, sm.buf[b] + (size_t)r0 * LP * sizeof(V), pol_stream);
+                    tma::store_commit();
+                    tma::store_wait_read();
+                    tma::mbar_arrive(&sm.empty[b]);
+                }
+                tma::store_wait_all();
+            }
+        }
+    } else {
+        // ---- butterfly groups
+        const int group = tid / TMA_GROUP_THREADS, gtid = tid % TMA_GROUP_THREADS;
+        const int bar_id = 1 + group;
+        const int l = gtid % L, j = gtid / L;
+        const unsigned q = rank * (unsigned)L + (unsigned)l;
+        const V w0 = tma_twiddle<T>(ta, q * (unsigned)j);
+        const int row = gtid / TT2, jj = gtid % TT2;           // second half, first read: consecutive positions of one row
+        const int sw = (row & (SLOTS / TT2 - 1)) * TT2;
+        const int l2 = gtid % LP, j2 = gtid / LP;              // second half after its exchange: adjacent lanes, adjacent rows
+        for (unsigned t = (unsigned)group; t < my_lines; t += TMA_GROUPS) {
+            const int b = (int)(t % TMA_BUFFERS);
+            const unsigned par = (t / TMA_BUFFERS) & 1;
+            V *buf = reinterpret_cast<V *>(sm.buf[b]);
+            tma::mbar_wait(&sm.full[b], par);
+            V v[E];
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = buf[(j + c * TT1) * L + l];
+            TileA::stage_first(v, buf, nullptr, ta, l, j, l, j, a.tw_a, 0u, gtid, bar_id);
+            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // the whole group has read its tile for the last time
+            if (gtid == 0) {
+                // the bytes this block is about to receive, then "my buffer is free" to every block of the cluster
+                tma::mbar_arrive_expect_tx(&sm.landed[b], TMA_TILE_BYTES);
+                const unsigned fr = tma::smem_u32(&sm.free_[b]);
+#pragma unroll
+                for (unsigned p = 0; p < (unsigned)C; ++p) cl::mbar_arrive_remote(cl::map(fr, p));
+            }
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = cmul_tw<FWD>(v[c], c == 0 ? w0 : cmul(w0, sm.table[c * L + l]));
+            cl::mbar_wait_cluster(&sm.free_[b], par);
+            {
+                const unsigned local = tma::smem_u32(buf), lb = tma::smem_u32(&sm.landed[b]);
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    const unsigned k1 = (unsigned)(j + c * TT1);
+                    const unsigned dst = k1 / (unsigned)LP, r = k1 % (unsigned)LP;
+                    const unsigned pos = q ^ ((r & (unsigned)(SLOTS / TT2 - 1)) * (unsigned)TT2);
+                    cl::store_async(cl::map(local + (r * (unsigned)N2 + pos) * (unsigned)sizeof(V), dst), v[c], cl::map(lb, dst));
+                }
+            }
+            cl::mbar_wait_cluster(&sm.landed[b], par);
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = buf[row * N2 + ((jj + c * TT2) ^ sw)];
+            Dft<E, FWD, T>::run(v);
+            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // every thread has read the received rows
+#pragma unroll
+            for (int p = 0; p < E; ++p) buf[(jj * E + p) * LP + (row ^ (jj << SH))] = v[p];
+            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+#pragma unroll
+            for (int c = 0; c < E; ++c) v[c] = buf[(j2 + c * TT2) * LP + (l2 ^ (((c * TT2) >> LG_E) << SH))];
+            TileB::template stage<1>(v, buf, l2, j2, l2, j2, a.tw_b, bar_id);
+            if (a.do_scale) {
+                const T s = (T)a.scale;
+#pragma unroll
+                for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
+            }
+            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // every thread has read its last-stage inputs
+#pragma unroll
+            for (int c = 0; c < E; ++c) buf[(j2 + c * TT2) * LP + l2] = v[c];
+            tma::fence_async_smem();
+            tma::mbar_arrive(&sm.ready[b]);
+        }
+    }
+    // nobody leaves while a peer may still arrive on or write into its shared memory
+    cl::sync_all();
+}
+
 }  // namespace dscfft
 
 #endif  // !DSC_EMUL

@@ -193,8 +193,10 @@ template <> TmaEntry *tma_entry<double, false>(int, int);
 #if !defined(DSC_EMUL)
 struct ClusterEntry {
     void (*fn)(const CUtensorMap, const CUtensorMap, const ClusterArgs);
-    int lg_n1, lg_n2, l, lp, blocks, box_a, box_b, smem;
+    void (*fn_pipe)(const CUtensorMap, const CUtensorMap, const ClusterArgs, unsigned, unsigned);     // persistent, pipelined
+    int lg_n1, lg_n2, l, lp, blocks, box_a, box_b, smem, smem_pipe;
     int state;            // 0 = not configured yet, 1 = usable, -1 = this device cannot co-schedule the cluster
+    int state_pipe, clusters_pipe;      // same for the pipelined kernel; resident clusters of its persistent launch
 };
 
 template <typename T, bool FWD, int LG_N1, int LG_N2>
@@ -208,6 +210,10 @@ ClusterEntry make_cluster() {
     e.box_a = tma_box_rows(LG_N1); e.box_b = tma_box_rows(LG_N2);
     e.smem = (int)sizeof(ClusterSmem<T, LG_N1>) + 1024;
     e.state = 0;
+    e.fn_pipe = fft_cluster_pipe<T, LG_N1, LG_N2, FWD>;
+    e.smem_pipe = (int)sizeof(ClusterPipeSmem<T, LG_N1>) + 1024;
+    e.state_pipe = 0;
+    e.clusters_pipe = 0;
     return e;
 }
 

@@ -370,10 +370,12 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
     return check_launch("four_step_tma");
 }
-// Which line lengths (log2) go to the cluster kernel.  Measured on B200 (profiles/r2_two_pass_lengths.md): it reads and
-// writes exactly the algorithmic bytes, but with two 256-thread blocks per SM and two cluster barriers per line it is
-// latency-bound -- 3.16 TB/s at 2^15 (TMA-fed two-pass launch: 3.0), 2.7 at 2^16 (3.0), 2.2 at 2^17 (2.8), 3.5 at 2^14
-// (single-pass block: 4.3).  Default: 2^15 only.  DSC_CLUSTER_LGS=14,15,16,17 selects others (tests do), DSC_NO_CLUSTER=1 none.
+// Which line lengths (log2) go to the cluster kernels.  Measured on B200 (profiles/r2_two_pass_lengths.md): they read and
+// write exactly the algorithmic bytes, but the all-to-all between the blocks of a cluster couples every line to the
+// slowest of C SMs twice, and clusters of 8 leave 19 % of the SMs without a block: pipelined variant 3.28 TB/s at 2^15
+// (TMA-fed two-pass launch: 3.0), 2.46 at 2^16 (2.98), 1.97 at 2^17 (2.80), 3.85 at 2^14 (single-pass block: 4.30).
+// Default: 2^15 only.  DSC_CLUSTER_LGS=14,15,16,17 selects others (tests do), DSC_NO_CLUSTER=1 none; DSC_CLUSTER_PIPE=0
+// selects the one-line-per-cluster launch instead of the persistent pipelined one.
 inline bool cluster_wanted(const int lg_n) {
     static const unsigned mask = [] {
         const char *off = getenv("DSC_NO_CLUSTER");
@@ -438,6 +440,30 @@ int cluster_launch(const dsc_cuda_plan *p, const void *x, long long x_row_stride
     a.tw_lo = p->col_lo; a.tw_hi = p->col_hi;
     a.four_shift = p->col_shift; a.four_mask = (1 << p->col_shift) - 1;
     a.do_scale = scale; a.scale = 1.0 / (double)n;
+    // the pipelined variant: persistent clusters, three tile buffers per block, mbarrier-signalled DSMEM stores
+    static const bool want_pipe = [] { const char *e = getenv("DSC_CLUSTER_PIPE"); return e == nullptr || *e == '\0' || *e != '0'; }();
+    if (want_pipe && ce->state_pipe >= 0 && rows < 0x7fffffffLL) {
+        cudaLaunchConfig_t pc = cfg;
+        pc.blockDim = dim3(TMA_THREADS, 1, 1);
+        pc.dynamicSmemBytes = (size_t)ce->smem_pipe;
+        if (ce->state_pipe == 0) {
+            cudaError_t err = cudaFuncSetAttribute((const void *)ce->fn_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, ce->smem_pipe);
+            if (err == cudaSuccess && ce->blocks > 8)
+                err = cudaFuncSetAttribute((const void *)ce->fn_pipe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            int clusters = 0;
+            pc.gridDim = dim3((unsigned)(ce->blocks * 1024), 1, 1);
+            if (err == cudaSuccess) err = cudaOccupancyMaxActiveClusters(&clusters, (const void *)ce->fn_pipe, &pc);
+            if (err != cudaSuccess || clusters < 1) { cudaGetLastError(); ce->state_pipe = -1; }
+            else { ce->state_pipe = 1; ce->clusters_pipe = clusters; }
+        }
+        if (ce->state_pipe == 1) {
+            const unsigned clusters = (unsigned)(rows < ce->clusters_pipe ? rows : ce->clusters_pipe);
+            pc.gridDim = dim3(clusters * (unsigned)ce->blocks, 1, 1);
+            const cudaError_t le = cudaLaunchKernelEx(&pc, ce->fn_pipe, map_x, map_out, a, (unsigned)rows, clusters);
+            if (le != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "fft_cluster_pipe: %s", cudaGetErrorString(le));
+            return check_launch("fft_cluster_pipe");
+        }
+    }
     const cudaError_t le = cudaLaunchKernelEx(&cfg, ce->fn, map_x, map_out, a);
     if (le != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "fft_cluster: %s", cudaGetErrorString(le));
     return check_launch("fft_cluster");
