@@ -32,6 +32,7 @@
 #if !defined(DSC_EMUL)
 
 #include <cuda.h>
+#include <cstdio>
 
 #include "dsc_cuda.h"
 #include "fft_kernels.cuh"
@@ -69,8 +70,18 @@ DSC_DEV bool mbar_test_wait(void *bar, unsigned parity) {       // never suspend
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-DSC_DEV void mbar_wait(void *bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+// Watchdog of every wait in these kernels: a wait that has not been satisfied after 2^32 cycles (two seconds) is a
+// protocol bug or a lost peer, not load -- say which one and stop the launch instead of hanging the device.
+DSC_DEV void wait_timeout(const char *what, const void *bar, unsigned parity) {
+    printf("dsc(cuda): block %u thread %u stuck in %s (barrier smem+0x%x, parity %u)\n", blockIdx.x, threadIdx.x, what,
+           smem_u32(bar), parity);
+    __trap();
+}
+DSC_DEV void mbar_wait(void *bar, unsigned parity, const char *what = "mbarrier wait") {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > (1LL << 32)) wait_timeout(what, bar, parity);
 }
 DSC_DEV void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (a following bulk store reads them)
@@ -148,7 +159,9 @@ template <typename T> struct TmaSmem {
     unsigned long long full[TMA_BUFFERS];          // bytes of the tile have landed (producer + TMA -> consumers)
     unsigned long long ready[TMA_BUFFERS];         // the finished tile lies in the buffer (consumers -> storer)
     unsigned long long empty[TMA_BUFFERS];         // the store has read the buffer (storer -> loader)
+    unsigned long long posted[TMA_BUFFERS];        // desc[b] names the tile that is on its way (loader -> groups)
     TmaTileDesc desc[TMA_BUFFERS];
+    V ladder[2][5 * 32];                           // the stage-1 twiddle rows of the two passes (TmaTile::ladder_fill)
 };
 
 // W_n^p from the two sqrt(n)-sized tables
@@ -191,9 +204,29 @@ struct TmaTile {
         }
     }
 
+        // lad: optional shared-memory copy of the rows of the stage-1 table a butterfly loads (ladder_rows() of them, row r =
+    // table row 2^r - 1 when the ladder is used, else row r), see ladder_fill(); nullptr = read the table in global memory
+    static constexpr int LADDER_R1 = STAGES >= 2 ? (1 << Sc::lg_r(1)) : 1;
+    static constexpr bool LADDER_POW2 = LADDER_R1 >= 8;
+    static constexpr int ladder_rows() {
+        int r = 0;
+        if (LADDER_POW2) { for (int m = 1; m < LADDER_R1; m *= 2) ++r; } else r = LADDER_R1 - 1;
+        return r;
+    }
+    static constexpr int LADDER_ELEMS = ladder_rows() * E;        // stage 1: NS = E entries per row
+    static DSC_DEV void ladder_fill(V *lad, const void *const *tw_all, const int tid, const int threads) {
+        if constexpr (STAGES >= 2) {
+            const V *__restrict__ tw = (const V *)tw_all[1];
+            for (int i = tid; i < LADDER_ELEMS; i += threads) {
+                const int r = i / E, k = i % E;
+                const int m = LADDER_POW2 ? (1 << r) : r + 1;
+                lad[i] = __ldg(tw + (m - 1) * E + k);
+            }
+        }
+    }
     template <int S>
     static DSC_DEV void stage(V (&v)[E], V *buf, const int l, const int j, const int l_last, const int j_last,
-                              const void *const *tw_all, const int bar_id) {
+                              const void *const *tw_all, const int bar_id, const V *lad = nullptr) {
         constexpr int LG_R = Sc::lg_r(S), R = 1 << LG_R, NB = E / R;
         constexpr int LG_NS = S * LG_E, NS = 1 << LG_NS;
         constexpr bool LAST = S == STAGES - 1;
@@ -211,8 +244,11 @@ struct TmaTile {
                     V w[R];
 #pragma unroll
                     for (int m = 1; m < R; ++m) {
-                        if ((m & (m - 1)) == 0) w[m] = __ldg(tw + (m - 1) * NS + k);
-                        else {
+                        if ((m & (m - 1)) == 0) {
+                            int r = 0;
+                            while ((1 << r) < m) ++r;
+                            w[m] = (S == 1 && lad != nullptr) ? lad[r * NS + k] : __ldg(tw + (m - 1) * NS + k);
+                        } else {
                             int hi = 1;
                             while (hi * 2 <= m) hi *= 2;
                             w[m] = cmul(w[hi], w[m - hi]);
@@ -221,7 +257,8 @@ struct TmaTile {
                     }
                 } else {
 #pragma unroll
-                    for (int m = 1; m < R; ++m) r[m] = cmul_tw<FWD>(r[m], __ldg(tw + (m - 1) * NS + k));
+                    for (int m = 1; m < R; ++m)
+                        r[m] = cmul_tw<FWD>(r[m], (S == 1 && lad != nullptr) ? lad[(m - 1) * NS + k] : __ldg(tw + (m - 1) * NS + k));
                 }
             }
             Dft<R, FWD, T>::run(r);
@@ -240,27 +277,38 @@ struct TmaTile {
             const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
-            stage<S + 1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id);
+            stage<S + 1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id, lad);
         }
     }
 
     // buf: the tile as the box delivered it, [position][line]; on return the finished tile, [line][position]
     // (TRANSPOSE, times the inter-pass twiddle W_n^(q k1)) or [position][line] (times the inverse's 1/n).
+    // Inter-pass twiddles of a TRANSPOSE tile, W_n^(q k1) with k1 = j + c TT: W^(q j) per thread (returned) and W^(q TT c)
+    // in a (c, line) table of the tile.  Depends on the tile's position only, so the launch calls it as soon as the tile's
+    // descriptor is known, while the tile itself is still travelling.  The group barrier keeps the previous tile's readers
+    // of the table ahead of its new contents.
+    static DSC_DEV V prepare(V *table, const TmaArgs &a, const unsigned q0, const int gtid, const int bar_id) {
+        const int l_last = gtid / TT, j_last = gtid % TT;
+        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+        for (int i = gtid; i < L * E; i += TMA_GROUP_THREADS) {
+            const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
+            table[i] = tma_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
+        }
+        return tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
+    }
+
     static DSC_DEV void run(V *buf, V *table, const TmaArgs &a, const void *const *tw_all, const unsigned q0,
-                            const int gtid, const int bar_id) {
+                            const int gtid, const int bar_id, const V *lad = nullptr, const bool prepared = false,
+                            V w0 = V{}) {
         const int l = gtid % L, j = gtid / L;
         const int l_last = TRANSPOSE ? gtid / TT : l, j_last = TRANSPOSE ? gtid % TT : j;
         V v[E];
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = buf[(j + c * TT) * L + l];
-        V w0 = mk<T>((T)1, (T)0);
         if constexpr (TRANSPOSE) {
-            // k1 = j + c TT: W^(q j) per thread, W^(q TT c) from a (c, line) table of the tile.  The previous tile's
-            // readers of the table are past this tile's first barrier only after they finished with it, so the table
-            // is rebuilt AFTER that barrier: between the scatter and the exchange barrier of the first stage.
-            w0 = tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
+            if (!prepared) w0 = tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
         }
-        stage_first(v, buf, table, a, l, j, l_last, j_last, tw_all, q0, gtid, bar_id);
+        stage_first(v, buf, table, a, l, j, l_last, j_last, tw_all, q0, gtid, bar_id, lad, prepared);
         // every thread has read its last-stage inputs: the buffer may take the finished tile
         dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
         if constexpr (TRANSPOSE) {
@@ -283,7 +331,7 @@ struct TmaTile {
     // stage 0 with the table build folded in after its first barrier
     static DSC_DEV void stage_first(V (&v)[E], V *buf, V *table, const TmaArgs &a, const int l, const int j,
                                     const int l_last, const int j_last, const void *const *tw_all, const unsigned q0,
-                                    const int gtid, const int bar_id) {
+                                    const int gtid, const int bar_id, const V *lad = nullptr, const bool prepared = false) {
         static_assert(STAGES >= 2, "a pass has at least one exchange");
         constexpr int R = 1 << Sc::lg_r(0), NB = E / R;
         static_assert(NB == 1, "the first stage is a full-radix butterfly");
@@ -294,16 +342,18 @@ struct TmaTile {
 #pragma unroll
         for (int p = 0; p < R; ++p) buf[phys<NEXT_JFAST>(base + p, l)] = v[p];
         if constexpr (TRANSPOSE) {
-            for (int i = gtid; i < L * E; i += TMA_GROUP_THREADS) {
-                const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
-                table[i] = tma_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
+            if (!prepared) {
+                for (int i = gtid; i < L * E; i += TMA_GROUP_THREADS) {
+                    const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
+                    table[i] = tma_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
+                }
             }
         }
         dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
         const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
-        stage<1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id);
+        stage<1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id, lad);
     }
 };
 
@@ -338,9 +388,13 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             tma::mbar_init(&sm.full[b], 1);
             tma::mbar_init(&sm.ready[b], TMA_GROUP_THREADS);
             tma::mbar_init(&sm.empty[b], 1);
+            tma::mbar_init(&sm.posted[b], 1);
         }
         tma::fence_barrier_init();
     }
+    static_assert(TileA::LADDER_ELEMS <= 5 * 32 && TileB::LADDER_ELEMS <= 5 * 32, "ladder rows");
+    TileA::ladder_fill(sm.ladder[0], a.tw_a, tid, TMA_THREADS);
+    TileB::ladder_fill(sm.ladder[1], a.tw_b, tid, TMA_THREADS);
     __syncthreads();
 
     const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
@@ -371,21 +425,31 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     if (!role_a) { flag = s.a_done + row; target = (unsigned)s.tiles_a; }
                     else if (s.ring && row >= (unsigned)s.ring) { flag = s.b_done + (row - s.ring); target = (unsigned)s.tiles_b; }
                     if (flag != nullptr) {
-                        while (ld_acquire(flag) < target) __nanosleep(64);
+                        const long long t0 = clock64();
+                        while (ld_acquire(flag) < target) {
+                            __nanosleep(64);
+                            if (clock64() - t0 > (1LL << 32)) {
+                                printf("dsc(cuda): block %u loader stuck on the row counter of %s row %u (have %u, need %u), ticket %u\n",
+                                       blockIdx.x, role_a ? "second-pass" : "first-pass", role_a ? row - s.ring : row, ld_acquire(flag), target, ticket);
+                                __trap();
+                            }
+                        }
                         tma::fence_async_all();
                     }
                 }
                 // the buffer: the store of tile t - 3 has read it
                 const int b = (int)(t % TMA_BUFFERS);
-                if (t >= TMA_BUFFERS) tma::mbar_wait(&sm.empty[b], (t / TMA_BUFFERS - 1) & 1);
+                if (t >= TMA_BUFFERS) tma::mbar_wait(&sm.empty[b], (t / TMA_BUFFERS - 1) & 1, "loader: empty");
                 if (exit) {
                     // no more tiles: one more turn for each group (and the storer), then leave
                     sm.desc[b] = TmaTileDesc{0u, 0u, 0u, 1u};
+                    tma::mbar_arrive(&sm.posted[b]);
                     tma::mbar_arrive(&sm.full[b]);
                     if (++exits_posted == TMA_GROUPS) break;
                     continue;
                 }
                 sm.desc[b] = TmaTileDesc{role_a ? 1u : 0u, row, r, 0u};
+                tma::mbar_arrive(&sm.posted[b]);
                 tma::mbar_arrive_expect_tx(&sm.full[b], TMA_TILE_BYTES);
                 if (role_a) {
                     constexpr int ROWS = 1 << LG_N1;
@@ -421,7 +485,7 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 const unsigned par = (st / TMA_BUFFERS) & 1;
                 if (!tma::mbar_test_wait(&sm.ready[b], par)) {
                     publish(0);                         // nothing to do anyway: other blocks may be waiting for these
-                    tma::mbar_wait(&sm.ready[b], par);
+                    tma::mbar_wait(&sm.ready[b], par, "storer: ready");
                 }
                 const TmaTileDesc d = sm.desc[b];
                 if (d.exit) {
@@ -456,12 +520,17 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const int bar_id = 1 + group;
     for (unsigned t = (unsigned)group;; t += TMA_GROUPS) {
         const int b = (int)(t % TMA_BUFFERS);
-        tma::mbar_wait(&sm.full[b], (t / TMA_BUFFERS) & 1);
+        // the descriptor arrives with the load's issue: twiddles that depend on the tile's position only are built while
+        // the tile is still on its way
+        tma::mbar_wait(&sm.posted[b], (t / TMA_BUFFERS) & 1, "group: posted");
         const TmaTileDesc d = sm.desc[b];
+        V w0 = mk<T>((T)1, (T)0);
+        if (d.role_a && !d.exit) w0 = TileA::prepare(sm.table[group], a, d.r * (unsigned)L_A, gtid, bar_id);
+        tma::mbar_wait(&sm.full[b], (t / TMA_BUFFERS) & 1, "group: full");
         if (d.exit) { tma::mbar_arrive(&sm.ready[b]); break; }
         V *buf = reinterpret_cast<V *>(sm.buf[b]);
-        if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id);
-        else TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id);
+        if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id, sm.ladder[0], true, w0);
+        else TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id, sm.ladder[1]);
         tma::fence_async_smem();
         tma::mbar_arrive(&sm.ready[b]);
     }
