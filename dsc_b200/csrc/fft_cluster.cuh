@@ -341,7 +341,7 @@ fft_cluster_pipe(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = buf[(j + c * TT1) * L + l];
             TileA::stage_first(v, buf, nullptr, ta, l, j, l, j, a.tw_a, 0u, gtid, bar_id);
-            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // the whole group has read its tile for the last time
+            dsc_group_barrier(bar_id, TMA_GROUP_THREADS);        // the whole group has read its tile for the last time
             if (gtid == 0) {
                 // the bytes this block is about to receive, then "my buffer is free" to every block of the cluster
                 tma::mbar_arrive_expect_tx(&sm.landed[b], TMA_TILE_BYTES);
@@ -366,10 +366,10 @@ fft_cluster_pipe(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = buf[row * N2 + ((jj + c * TT2) ^ sw)];
             Dft<E, FWD, T>::run(v);
-            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // every thread has read the received rows
+            dsc_group_barrier(bar_id, TMA_GROUP_THREADS);        // every thread has read the received rows
 #pragma unroll
             for (int p = 0; p < E; ++p) buf[(jj * E + p) * LP + (row ^ (jj << SH))] = v[p];
-            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+            dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = buf[(j2 + c * TT2) * LP + (l2 ^ (((c * TT2) >> LG_E) << SH))];
             TileB::template stage<1>(v, buf, l2, j2, l2, j2, a.tw_b, bar_id);
@@ -378,7 +378,7 @@ fft_cluster_pipe(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                 for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
             }
-            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // every thread has read its last-stage inputs
+            dsc_group_barrier(bar_id, TMA_GROUP_THREADS);        // every thread has read its last-stage inputs
 #pragma unroll
             for (int c = 0; c < E; ++c) buf[(j2 + c * TT2) * LP + l2] = v[c];
             tma::fence_async_smem();

@@ -149,6 +149,9 @@ template <> FusedEntry *fused_entry<double, false>(int, int);
 #if !defined(DSC_EMUL)
 struct TmaEntry {
     void (*fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
+    // float passes of <= 512 points: 16 points per thread on 32 KiB tiles (half the lines per tile), two blocks per SM
+    void (*fn16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
+    int smem16, ctas16;
     int lg_n1, lg_n2, l_a, l_b, box_a, box_b, smem;
     int grid;
     bool configured;
@@ -158,6 +161,11 @@ template <typename T, bool FWD, int LG_N1, int LG_N2>
 TmaEntry make_tma() {
     TmaEntry e;
     e.fn = four_step_tma<T, LG_N1, LG_N2, FWD>;
+    e.fn16 = nullptr; e.smem16 = 0; e.ctas16 = 0;
+    if constexpr (sizeof(T) == 4 && LG_N1 <= 9 && LG_N2 <= 9) {
+        e.fn16 = four_step_tma<T, LG_N1, LG_N2, FWD, 4, TMA_TILE_BYTES / 2>;
+        e.smem16 = (int)sizeof(TmaSmem<T, TMA_TILE_BYTES / 2>) + 1024;
+    }
     e.lg_n1 = LG_N1; e.lg_n2 = LG_N2;
     e.l_a = tma_lines<T>(LG_N1); e.l_b = tma_lines<T>(LG_N2);
     e.box_a = tma_box_rows(LG_N1); e.box_b = tma_box_rows(LG_N2);

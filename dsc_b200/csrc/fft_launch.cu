@@ -67,6 +67,8 @@ struct PlanLayout {
     // column decomposition of long single-pass complex plans (transforms along a non-last axis)
     int col_lg_n1, col_lg_n2, col_shift, col_lg_e1, col_lg_e2;
     size_t off_ctw1[DSC_CUDA_MAX_STAGES], off_ctw2[DSC_CUDA_MAX_STAGES], off_clo, off_chi;
+    bool e16;                                   // float fused plans with factors <= 512: tables for 16 points per thread
+    size_t off_tw1_e16[DSC_CUDA_MAX_STAGES], off_tw2_e16[DSC_CUDA_MAX_STAGES];
     bool ok;
 };
 
@@ -97,6 +99,12 @@ template <typename T> PlanLayout plan_layout(int n, int fft_type) {
         L.four_shift = (L.lg_n + 1) / 2;
         L.off_lo = take((size_t)1 << L.four_shift);
         L.off_hi = take((size_t)1 << (L.lg_n - L.four_shift));
+    }
+    L.e16 = sizeof(T) == 4 && fused && L.lg_n1 <= 9 && L.lg_n2 <= 9;
+    if (L.e16) {
+        const SubSched a1 = sub_sched(L.lg_n1, 4), a2 = sub_sched(L.lg_n2, 4);
+        for (int s = 1; s < a1.stages; ++s) L.off_tw1_e16[s] = take((size_t)(a1.r[s] - 1) * a1.ns[s]);
+        for (int s = 1; s < a2.stages; ++s) L.off_tw2_e16[s] = take((size_t)(a2.r[s] - 1) * a2.ns[s]);
     }
     if (L.lg_n2 == 0 && fft_type == DSC_CUDA_FFT_COMPLEX && L.lg_n >= columns_min_lg<T>()) {
         L.col_lg_n2 = L.lg_n / 2;
@@ -151,6 +159,11 @@ int build_tables(dsc_cuda_plan *p, const PlanLayout &L, void *stream) {
         p->tw_hi = base + L.off_hi;
         fill_pow(p->tw_lo, 1LL << L.four_shift, 1, n);
         fill_pow(p->tw_hi, 1LL << (L.lg_n - L.four_shift), 1LL << L.four_shift, n);
+    }
+    if (L.e16) {
+        const SubSched a1 = sub_sched(L.lg_n1, 4), a2 = sub_sched(L.lg_n2, 4);
+        for (int s = 1; s < a1.stages; ++s) { p->tw1_e16[s] = base + L.off_tw1_e16[s]; fill_stage(p->tw1_e16[s], a1.ns[s], a1.r[s]); }
+        for (int s = 1; s < a2.stages; ++s) { p->tw2_e16[s] = base + L.off_tw2_e16[s]; fill_stage(p->tw2_e16[s], a2.ns[s], a2.r[s]); }
     }
     if (L.lg_n2) {
         // a two-pass plan is its own column decomposition
@@ -303,6 +316,11 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
     TmaEntry *te = tma_entry<T, FWD>(p->lg_n1, p->lg_n2);
     if (te == nullptr || tma_disabled()) return 1;
+    // 16 points per thread on 32 KiB tiles, two blocks per SM (twice the butterfly warps), where the plan carries its tables.
+    // Measured on B200: 2914 / 2778 / 2580 / 2508 GB/s at 2^15 .. 2^18 against 3060 / 2994 / 2844 / 2739 for 32 points per
+    // thread -- doubling the warps does not help, so it is opt-in (DSC_TMA_E16=1; the GPU parity tests run it).
+    static const bool want_e16 = [] { const char *e = getenv("DSC_TMA_E16"); return e != nullptr && *e == '1'; }();
+    bool e16 = te->fn16 != nullptr && p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr && want_e16;
     // dense complex rows, read in full, 16-byte aligned rows on both sides
     if (first.in_kind != IN_COMPLEX || first.in_limit < n || first.seg_shift != 0 || first.gi.lstride != 1 || first.gi.estride != n2 ||
         first.ring_in != 0 || (uintptr_t)first.x % 16 != 0 || (uintptr_t)dst % 16 != 0 ||
@@ -314,6 +332,12 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     if (work == nullptr || work_bytes < sync_bytes + row_bytes || (uintptr_t)work % 256 != 0) return 1;
     if (!te->configured) {
         cudaError_t err = cudaFuncSetAttribute((const void *)te->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
+        if (err == cudaSuccess && te->fn16 != nullptr) {
+            err = cudaFuncSetAttribute((const void *)te->fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem16);
+            int per_sm = 0;
+            if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)te->fn16, TMA_THREADS, te->smem16);
+            te->ctas16 = per_sm;
+        }
         int dev = 0, sms = 0;
         if (err == cudaSuccess) err = cudaGetDevice(&dev);
         if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -321,8 +345,11 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
         te->grid = sms;                       // one block (two butterfly groups + the producer warp) per SM
         te->configured = true;
     }
-    const long long tiles_a = n2 / te->l_a, tiles_b = n1 / te->l_b;
+    if (e16 && te->ctas16 < 1) e16 = false;
+    const int l_a = e16 ? te->l_a / 2 : te->l_a, l_b = e16 ? te->l_b / 2 : te->l_b;
+    const long long tiles_a = n2 / l_a, tiles_b = n1 / l_b;
     if (rows * (tiles_a + tiles_b) >= 0x7fffffffLL) return 1;
+    const long long resident = e16 ? (long long)te->ctas16 * te->grid : te->grid;      // blocks on the device at once
     long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
     static const size_t ring_budget = [] { const char *e = getenv("DSC_TMA_RING_MB"); return (size_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20; }();
     const long long cap = (long long)(ring_budget / row_bytes) > 4 ? (long long)(ring_budget / row_bytes) : 4;
@@ -339,7 +366,7 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     {
         // a tile is published about four tile times after its ticket was taken, while the whole GPU takes
         // ~grid tickets per tile time: put a row's second pass that far behind its first pass
-        long long lag = (4LL * te->grid + tiles_b + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
+        long long lag = (4LL * resident + tiles_b + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
         if (lag < 1) lag = 1;
         if (ring > 0 && lag > ring / 2) lag = ring / 2;
         if (lag > rows) lag = rows;
@@ -349,16 +376,19 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     CUtensorMap map_x, map_w, map_out;
     const unsigned long long wrows = (unsigned long long)(ring ? ring : rows);
     if (!encode_3d(&map_x, first.x, sizeof(V), (unsigned long long)n2, (unsigned long long)n1, (unsigned long long)rows,
-                   (unsigned long long)n2, (unsigned long long)first.gi.ostride, (unsigned)te->l_a, (unsigned)te->box_a) ||
+                   (unsigned long long)n2, (unsigned long long)first.gi.ostride, (unsigned)l_a, (unsigned)te->box_a) ||
         !encode_3d(&map_w, mid, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, wrows,
-                   (unsigned long long)n1, (unsigned long long)n, (unsigned)te->l_b, (unsigned)te->box_b) ||
+                   (unsigned long long)n1, (unsigned long long)n, (unsigned)l_b, (unsigned)te->box_b) ||
         !encode_3d(&map_out, dst, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, (unsigned long long)rows,
-                   (unsigned long long)n1, (unsigned long long)dst_row_stride, (unsigned)te->l_b, (unsigned)te->box_b))
+                   (unsigned long long)n1, (unsigned long long)dst_row_stride, (unsigned)l_b, (unsigned)te->box_b))
         return 1;
     TmaArgs a{};
     a.work = mid;
     a.ring = ring;
-    for (int i = 0; i < DSC_CUDA_MAX_STAGES; ++i) { a.tw_a[i] = p->tw1[i]; a.tw_b[i] = p->tw2[i]; }
+    for (int i = 0; i < DSC_CUDA_MAX_STAGES; ++i) {
+        a.tw_a[i] = e16 ? p->tw1_e16[i] : p->tw1[i];
+        a.tw_b[i] = e16 ? p->tw2_e16[i] : p->tw2[i];
+    }
     a.tw_lo = p->tw_lo; a.tw_hi = p->tw_hi;
     a.four_shift = p->four_shift; a.four_mask = (1 << p->four_shift) - 1;
     a.do_scale = scale; a.scale = 1.0 / (double)n;
@@ -366,8 +396,9 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
     if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
     const long long tiles = rows * (tiles_a + tiles_b);
-    const unsigned blocks = (unsigned)(tiles < te->grid ? tiles : te->grid);
-    te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
+    if (e16) te->fn16<<<blocks, TMA_THREADS, te->smem16, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    else te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
     return check_launch("four_step_tma");
 }
 // Which line lengths (log2) go to the cluster kernels.  Measured on B200 (profiles/r2_two_pass_lengths.md): they read and

@@ -22,9 +22,16 @@ namespace dscfft {
 // bar.sync on one of the 16 hardware barriers for a subset of the block's warps
 #if defined(DSC_EMUL)
 #define dsc_named_barrier(id, count) __syncthreads()   /* every line runs the same sequence: a block barrier is equivalent */
+#define dsc_group_barrier(id, count) __syncthreads()
 #else
 __device__ __forceinline__ void dsc_named_barrier(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// the same for callers that only ever use barriers 1 and 2: with immediate barrier numbers ptxas reserves three hardware
+// barriers for the block instead of all sixteen (which would keep a second block off the SM)
+__device__ __forceinline__ void dsc_group_barrier(int id, int count) {
+    if (id == 1) asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(count) : "memory");
 }
 #endif
 

@@ -151,10 +151,12 @@ struct TmaArgs {
 
 struct TmaTileDesc { unsigned role_a, row, r, exit; };
 
-template <typename T> struct TmaSmem {
+template <typename T, int TILE = TMA_TILE_BYTES> struct TmaSmem {
     using V = cx<T>;
-    static constexpr int TABLE_MAX = sizeof(T) == 4 ? 32 * 32 : 32 * 16;     // (c, line) inter-pass twiddles of one pass-A tile, per group
-    alignas(1024) unsigned char buf[TMA_BUFFERS][TMA_TILE_BYTES];
+    // (c, line) inter-pass twiddles of one pass-A tile, per group: lines x points per thread, at most 32 x 32 (float, 64 KiB
+    // tiles of 256-point passes), 32 x 16 for the half-size tiles and for double
+    static constexpr int TABLE_MAX = (sizeof(T) == 4 && TILE >= TMA_TILE_BYTES) ? 32 * 32 : 32 * 16;
+    alignas(1024) unsigned char buf[TMA_BUFFERS][TILE];
     V table[TMA_GROUPS][TABLE_MAX];
     unsigned long long full[TMA_BUFFERS];          // bytes of the tile have landed (producer + TMA -> consumers)
     unsigned long long ready[TMA_BUFFERS];         // the finished tile lies in the buffer (consumers -> storer)
@@ -172,17 +174,21 @@ template <typename T> DSC_DEV cx<T> tma_twiddle(const TmaArgs &a, const unsigned
 }
 
 // ---- one tile on one consumer group -----------------------------------------------------------------------
-template <typename T, int LG_N, int L, bool FWD, bool TRANSPOSE>
+template <typename T, int LG_N, int L, bool FWD, bool TRANSPOSE, int LGE = tma_lg_e<T>()>
 struct TmaTile {
     using V = cx<T>;
-    static constexpr int LG_E = tma_lg_e<T>() < LG_N ? tma_lg_e<T>() : LG_N;
+    static constexpr int LG_E = LGE < LG_N ? LGE : LG_N;
     using Sc = Sched<LG_N, LG_E>;
     static constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, STAGES = Sc::STAGES;
     static constexpr int SLOTS = 128 / (int)sizeof(V);           // elements of one 128-byte bank phase: 16 / 8
     static constexpr bool NARROW = L < SLOTS;                    // a phase spans two positions
     static_assert(L * TT == TMA_GROUP_THREADS, "a tile is one register tile per thread of the group");
     static_assert(L * 2 >= SLOTS, "lines of at least 64 bytes");
-    static_assert(!NARROW || (STAGES == 2 && LG_N == 2 * LG_E), "narrow tiles: two full-radix stages only");
+    // narrow tiles: the half flip by position bit LG_E separates the two positions of a phase for the radix-E scatter
+    // (E j + p), and bit 0 separates them for every access whose positions differ by one: the readers (j + c TT) and the
+    // scatter of a second full-radix stage (((jj - k) E) + k + E p, k = jj mod E)
+    static_assert(!NARROW || (STAGES == 2 && LG_N == 2 * LG_E) || (STAGES == 3 && LG_N > 2 * LG_E),
+                  "narrow tiles: full-radix first (and second) stage only");
     static constexpr int LG_TT = LG_N - LG_E;
     static constexpr int LG_SLOTS = SLOTS == 16 ? 4 : 3;
     static constexpr int SW_BITS = LG_TT < LG_SLOTS ? LG_TT : LG_SLOTS;
@@ -266,14 +272,14 @@ struct TmaTile {
 #pragma unroll
                 for (int p = 0; p < R; ++p) v[b + p * NB] = r[p];
             } else {
-                if (b == 0) dsc_named_barrier(bar_id, TMA_GROUP_THREADS);    // every thread has read the previous layout
+                if (b == 0) dsc_group_barrier(bar_id, TMA_GROUP_THREADS);    // every thread has read the previous layout
                 const int base = ((jj - k) << LG_R) + k;
 #pragma unroll
                 for (int p = 0; p < R; ++p) buf[phys<NEXT_JFAST>(base + p * NS, l)] = r[p];
             }
         }
         if constexpr (!LAST) {
-            dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+            dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
             const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
@@ -289,7 +295,7 @@ struct TmaTile {
     // of the table ahead of its new contents.
     static DSC_DEV V prepare(V *table, const TmaArgs &a, const unsigned q0, const int gtid, const int bar_id) {
         const int l_last = gtid / TT, j_last = gtid % TT;
-        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
         for (int i = gtid; i < L * E; i += TMA_GROUP_THREADS) {
             const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
             table[i] = tma_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
@@ -310,7 +316,7 @@ struct TmaTile {
         }
         stage_first(v, buf, table, a, l, j, l_last, j_last, tw_all, q0, gtid, bar_id, lad, prepared);
         // every thread has read its last-stage inputs: the buffer may take the finished tile
-        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
         if constexpr (TRANSPOSE) {
 #pragma unroll
             for (int c = 0; c < E; ++c) {
@@ -337,7 +343,7 @@ struct TmaTile {
         static_assert(NB == 1, "the first stage is a full-radix butterfly");
         constexpr bool NEXT_JFAST = TRANSPOSE && (1 == STAGES - 1);
         Dft<R, FWD, T>::run(v);
-        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);        // every thread of the group has read the delivered tile
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);        // every thread of the group has read the delivered tile
         const int base = j << Sc::lg_r(0);
 #pragma unroll
         for (int p = 0; p < R; ++p) buf[phys<NEXT_JFAST>(base + p, l)] = v[p];
@@ -349,7 +355,7 @@ struct TmaTile {
                 }
             }
         }
-        dsc_named_barrier(bar_id, TMA_GROUP_THREADS);
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
         const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
@@ -368,19 +374,27 @@ struct TmaTile {
 //                       -> once the store before it has COMPLETED, publish that tile's row counter.  Whenever the
 //                       next tile is not ready yet it first completes and publishes everything outstanding, so no
 //                       other block (or this block's loader) waits on a counter longer than a store takes.
-template <typename T, int LG_N1, int LG_N2, bool FWD>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+// LGE / TILE: points per thread (log2) and bytes per tile.  The default (32 points, 64 KiB, one block per SM) leaves an SM
+// 16 butterfly warps at 96 registers, and in-kernel clocks show a group then needs ~10 000 cycles per tile: the transform,
+// not the data movement, paces the launch.  With 16 points per thread the registers allow twice the
+// warps, but two 512-thread groups plus the copy warps exceed the 1024-thread block limit; so the 16-point variant runs on
+// 32 KiB tiles (groups stay 256 threads) with TWO blocks per SM: 32 butterfly warps, six tiles in flight.  It covers float
+// passes of up to 512 points (32-byte rows beyond that).
+template <typename T, int LG_N1, int LG_N2, bool FWD, int LGE = tma_lg_e<T>(), int TILE = TMA_TILE_BYTES>
+__global__ void __launch_bounds__(TMA_THREADS, (TILE * 2 <= TMA_TILE_BYTES ? 2 : 1))
 four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const __grid_constant__ CUtensorMap map_out, const TmaArgs a, const FourStepSync s) {
     using V = cx<T>;
-    constexpr int L_A = tma_lines<T>(LG_N1), L_B = tma_lines<T>(LG_N2);
+    constexpr int TMA_TILE_BYTES = TILE;           // shadows the default for everything below
+    constexpr int L_A = (TILE / (int)sizeof(V)) >> LG_N1, L_B = (TILE / (int)sizeof(V)) >> LG_N2;
     constexpr int BOX_A = tma_box_rows(LG_N1), BOX_B = tma_box_rows(LG_N2);
-    using TileA = TmaTile<T, LG_N1, L_A, FWD, true>;
-    using TileB = TmaTile<T, LG_N2, L_B, FWD, false>;
-    static_assert(L_A * TileA::E <= TmaSmem<T>::TABLE_MAX, "inter-pass table");
+    using TileA = TmaTile<T, LG_N1, L_A, FWD, true, LGE>;
+    using TileB = TmaTile<T, LG_N2, L_B, FWD, false, LGE>;
+    using Smem = TmaSmem<T, TILE>;
+    static_assert(L_A * TileA::E <= Smem::TABLE_MAX, "inter-pass table");
     DSC_DYN_SMEM(smem_raw);
     // the tile buffers want 1024-byte alignment (box destinations): round the dynamic window up
-    TmaSmem<T> &sm = *reinterpret_cast<TmaSmem<T> *>(smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u));
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u));
 
     const int tid = threadIdx.x;
     if (tid == 0) {

@@ -27,7 +27,8 @@ class Plan(C.Structure):
                 ("tw_real_lo", C.c_void_p), ("tw_real_hi", C.c_void_p), ("real_shift", C.c_int),
                 ("col_lg_n1", C.c_int), ("col_lg_n2", C.c_int), ("col_shift", C.c_int),
                 ("col_tw1", C.c_void_p * MAX_STAGES), ("col_tw2", C.c_void_p * MAX_STAGES),
-                ("col_lo", C.c_void_p), ("col_hi", C.c_void_p)]
+                ("col_lo", C.c_void_p), ("col_hi", C.c_void_p),
+                ("tw1_e16", C.c_void_p * MAX_STAGES), ("tw2_e16", C.c_void_p * MAX_STAGES)]
 
 
 class DscCudaError(RuntimeError):

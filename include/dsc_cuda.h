@@ -67,6 +67,9 @@ typedef struct dsc_cuda_plan {
     int col_lg_n1, col_lg_n2, col_shift;
     void *col_tw1[DSC_CUDA_MAX_STAGES], *col_tw2[DSC_CUDA_MAX_STAGES];
     void *col_lo, *col_hi;
+    /* float two-pass plans with both factors <= 512: stage tables of the 16-points-per-thread schedule of the TMA-fed
+     * launch (the tw1 / tw2 tables above are laid out for 32 points per thread).  NULL otherwise. */
+    void *tw1_e16[DSC_CUDA_MAX_STAGES], *tw2_e16[DSC_CUDA_MAX_STAGES];
 } dsc_cuda_plan;
 
 const char *dsc_cuda_last_error(void);

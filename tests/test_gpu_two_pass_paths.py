@@ -2,6 +2,7 @@
    default      TMA-fed two-pass launch (fft_tma.cuh), thread-block clusters for 2^15-point lines (fft_cluster.cuh)
    clusters     one line per cluster for 2^14 .. 2^17 (2, 4, 8 and 16 blocks, distributed shared memory)
    registers    the register-direct persistent launch (four_step_fused), no TMA, no clusters
+   tma-e16      the TMA-fed launch with 16 points per thread on 32 KiB tiles, two blocks per SM (opt-in variant)
 The selection is made through environment variables the library reads once, hence one subprocess per variant."""
 import os
 import subprocess
@@ -16,10 +17,12 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,env", [("default", {}), ("clusters", {"DSC_CLUSTER_LGS": "14,15,16,17"}),
-                                      ("registers", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1"})])
+                                      ("clusters-unpipelined", {"DSC_CLUSTER_LGS": "14,15,16,17", "DSC_CLUSTER_PIPE": "0"}),
+                                      ("registers", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1"}),
+                                      ("tma-e16", {"DSC_TMA_E16": "1", "DSC_NO_CLUSTER": "1"})])
 def test_two_pass_paths(name, env):
     e = dict(os.environ)
-    for k in ("DSC_NO_TMA", "DSC_NO_CLUSTER", "DSC_CLUSTER_LGS"):
+    for k in ("DSC_NO_TMA", "DSC_NO_CLUSTER", "DSC_CLUSTER_LGS", "DSC_TMA_E16", "DSC_CLUSTER_PIPE"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, WORKER], capture_output=True, text=True, timeout=600, env=e)
