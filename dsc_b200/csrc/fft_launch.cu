@@ -393,6 +393,8 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     a.four_shift = p->four_shift; a.four_mask = (1 << p->four_shift) - 1;
     a.do_scale = scale; a.scale = 1.0 / (double)n;
     a.keep_out = keep_out;
+    static const bool no_discard = [] { const char *e = getenv("DSC_TMA_NO_DISCARD"); return e != nullptr && *e == '1'; }();
+    a.discard_work = !no_discard;
     const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
     if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
     const long long tiles = rows * (tiles_a + tiles_b);
