@@ -79,6 +79,28 @@ template <typename V> DSC_DEV V cmul(V a, V b) {
     V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }
 
+#if defined(DSC_F32X2) && !defined(DSC_EMUL)
+// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100): one instruction per complex add, two per complex multiply.
+// The FP32 pipe does the same lane-work either way, but the kernels that define DSC_F32X2 are bound by instruction ISSUE
+// (two-pass transforms: ~75 instructions per point, 57 % of the issue slots at the power-capped clock), and these halve
+// the floating-point instruction count.  Non-template overloads: preferred over the generic templates for float2.
+DSC_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DSC_DEV float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+DSC_DEV float2 cmul(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+}
+template <bool FWD> DSC_DEV float2 cmul_tw(float2 a, float2 w) {
+    if (FWD) return __ffma2_rn(make_float2(a.x, a.x), w, __fmul2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x)));
+    return __ffma2_rn(make_float2(a.x, a.x), make_float2(w.x, -w.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(w.y, w.x)));
+}
+// a * (c -+ i s): the constant rotations of the radix-8/16/32 butterflies
+template <bool FWD> DSC_DEV float2 crot(float2 a, const float c, const float s) {
+    return FWD ? __ffma2_rn(a, make_float2(c, c), __fmul2_rn(make_float2(a.y, a.x), make_float2(s, -s)))
+               : __ffma2_rn(a, make_float2(c, c), __fmul2_rn(make_float2(a.y, a.x), make_float2(-s, s)));
+}
+#define DSC_HAVE_CROT 1
+#endif
+
 // a * (-i) forward, a * (+i) inverse
 template <bool FWD, typename V> DSC_DEV V rot90(V a) {
     V r;
@@ -97,6 +119,12 @@ template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w8(cx<T> a) {
     constexpr T h = consts<T>::sqrt1_2;
     if (Q == 0) return a;
     if (Q == 2) return rot90<FWD>(a);
+#if defined(DSC_HAVE_CROT)
+    if constexpr (sizeof(T) == 4) {
+        if (Q == 1) return crot<FWD>(a, h, h);          // (1 -+ i) / sqrt 2
+        return crot<FWD>(a, -h, h);                     // (-1 -+ i) / sqrt 2
+    }
+#endif
     if (Q == 1) return FWD ? mk<T>((a.x + a.y) * h, (a.y - a.x) * h)
                            : mk<T>((a.x - a.y) * h, (a.x + a.y) * h);
     /* Q == 3 */ return FWD ? mk<T>((a.y - a.x) * h, -(a.x + a.y) * h)
@@ -110,6 +138,9 @@ template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w16(cx<T> a) {
     // odd q: cos/sin of q*pi/8 from the pi/8 pair
     constexpr T c = (Q == 1) ? c1 : (Q == 3) ? s1 : (Q == 5) ? -s1 : (Q == 7) ? -c1 : (Q == 9) ? -c1 : /*11*/ -s1;
     constexpr T s = (Q == 1) ? s1 : (Q == 3) ? c1 : (Q == 5) ? c1 : (Q == 7) ? s1 : (Q == 9) ? -s1 : /*11*/ -c1;
+#if defined(DSC_HAVE_CROT)
+    if constexpr (sizeof(T) == 4) return crot<FWD>(a, c, s);
+#endif
     return FWD ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s)
                : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
 }
@@ -198,6 +229,9 @@ template <bool FWD, int Q, typename T> DSC_DEV cx<T> mul_w32(cx<T> a) {
     if constexpr (Q % 2 == 0) return mul_w16<FWD, Q / 2, T>(a);
     else {
         constexpr T c = w32<T>::cosq(Q), s = w32<T>::sinq(Q);
+#if defined(DSC_HAVE_CROT)
+        if constexpr (sizeof(T) == 4) return crot<FWD>(a, c, s);
+#endif
         return FWD ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s)
                    : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
     }
