@@ -152,6 +152,9 @@ struct TmaEntry {
     // float passes of <= 512 points: 16 points per thread on 32 KiB tiles (half the lines per tile), two blocks per SM
     void (*fn16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
     int smem16, ctas16;
+    // the packed-real bin-pair step fused in: forward launches un-mix in the second pass (runs of at least 64 bytes);
+    // inverse launches (double: float bin rows have an odd pitch no tensor map takes) mix in the first pass
+    void (*fn_real)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
     int lg_n1, lg_n2, l_a, l_b, box_a, box_b, smem;
     int grid;
     bool configured;
@@ -166,6 +169,11 @@ TmaEntry make_tma() {
         e.fn16 = four_step_tma<T, LG_N1, LG_N2, FWD, 4, TMA_TILE_BYTES / 2>;
         e.smem16 = (int)sizeof(TmaSmem<T, TMA_TILE_BYTES / 2>) + 1024;
     }
+    e.fn_real = nullptr;
+    if constexpr (FWD && (tma_lines<T>(LG_N2) / 2) * (int)sizeof(cx<T>) >= 64)
+        e.fn_real = four_step_tma<T, LG_N1, LG_N2, FWD, tma_lg_e<T>(), TMA_TILE_BYTES, 1>;
+    if constexpr (!FWD && sizeof(T) == 8 && (tma_lines<T>(LG_N1) / 2) * (int)sizeof(cx<T>) >= 64 && (1 << LG_N1) / 2 <= TMA_GROUP_THREADS)
+        e.fn_real = four_step_tma<T, LG_N1, LG_N2, FWD, tma_lg_e<T>(), TMA_TILE_BYTES, 2>;
     e.lg_n1 = LG_N1; e.lg_n2 = LG_N2;
     e.l_a = tma_lines<T>(LG_N1); e.l_b = tma_lines<T>(LG_N2);
     e.box_a = tma_box_rows(LG_N1); e.box_b = tma_box_rows(LG_N2);

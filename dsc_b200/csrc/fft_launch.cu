@@ -308,19 +308,34 @@ inline bool tma_disabled() {
     return off;
 }
 
+// The packed-real bin-pair step fused into a TMA-fed launch (fft_tma.cuh, REAL): forward transforms leave as the bins
+// X[0..n] of the real transform (dst rows of pitch >= n + 1) or, with a spectrum, as the packed input z' of the inverse
+// transform of the fused filter.
+struct RealFuse {
+    const void *filt;          // forward: spectrum B[0..n], nullptr = rfft.  Inverse launches (irfft) read rows of n + 1 bins.
+};
+inline bool real_fuse_disabled() {
+    static const bool off = [] { const char *e = getenv("DSC_NO_REAL_FUSE"); return e != nullptr && *e != '\0' && *e != '0'; }();
+    return off;
+}
+
 // Returns 1 when the shape is not covered (the caller continues with four_step_fused), 0 on success, < 0 on error.
 template <typename T, bool FWD>
 int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long rows, void *work, size_t work_bytes,
-                         void *dst, long long dst_row_stride, bool scale, void *stream, bool keep_out) {
+                         void *dst, long long dst_row_stride, bool scale, void *stream, bool keep_out,
+                         const RealFuse *rf = nullptr) {
     using V = cx<T>;
     const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
     TmaEntry *te = tma_entry<T, FWD>(p->lg_n1, p->lg_n2);
     if (te == nullptr || tma_disabled()) return 1;
+    if (rf != nullptr && (te->fn_real == nullptr || real_fuse_disabled() || p->tw_real_lo == nullptr ||
+                          (FWD ? dst_row_stride < n + (rf->filt ? 0 : 1) : (first.in_limit < n + 1 || first.gi.ostride < n + 1))))
+        return 1;
     // 16 points per thread on 32 KiB tiles, two blocks per SM (twice the butterfly warps), where the plan carries its tables.
     // Measured on B200: 2914 / 2778 / 2580 / 2508 GB/s at 2^15 .. 2^18 against 3060 / 2994 / 2844 / 2739 for 32 points per
     // thread -- doubling the warps does not help, so it is opt-in (DSC_TMA_E16=1; the GPU parity tests run it).
     static const bool want_e16 = [] { const char *e = getenv("DSC_TMA_E16"); return e != nullptr && *e == '1'; }();
-    bool e16 = te->fn16 != nullptr && p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr && want_e16;
+    bool e16 = te->fn16 != nullptr && p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr && want_e16 && rf == nullptr;
     // dense complex rows, read in full, 16-byte aligned rows on both sides
     if (first.in_kind != IN_COMPLEX || first.in_limit < n || first.seg_shift != 0 || first.gi.lstride != 1 || first.gi.estride != n2 ||
         first.ring_in != 0 || (uintptr_t)first.x % 16 != 0 || (uintptr_t)dst % 16 != 0 ||
@@ -332,6 +347,8 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     if (work == nullptr || work_bytes < sync_bytes + row_bytes || (uintptr_t)work % 256 != 0) return 1;
     if (!te->configured) {
         cudaError_t err = cudaFuncSetAttribute((const void *)te->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
+        if (err == cudaSuccess && te->fn_real != nullptr)
+            err = cudaFuncSetAttribute((const void *)te->fn_real, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
         if (err == cudaSuccess && te->fn16 != nullptr) {
             err = cudaFuncSetAttribute((const void *)te->fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem16);
             int per_sm = 0;
@@ -375,12 +392,14 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     V *mid = (V *)((char *)work + sync_bytes);
     CUtensorMap map_x, map_w, map_out;
     const unsigned long long wrows = (unsigned long long)(ring ? ring : rows);
-    if (!encode_3d(&map_x, first.x, sizeof(V), (unsigned long long)n2, (unsigned long long)n1, (unsigned long long)rows,
-                   (unsigned long long)n2, (unsigned long long)first.gi.ostride, (unsigned)l_a, (unsigned)te->box_a) ||
+    const bool mix_in = rf != nullptr && !FWD;       // bin rows: n2 + 1 columns at a row pitch of n2 (the last one aliases the next row)
+    const bool unmix_out = rf != nullptr && FWD;
+    if (!encode_3d(&map_x, first.x, sizeof(V), (unsigned long long)(mix_in ? n2 + 1 : n2), (unsigned long long)n1, (unsigned long long)rows,
+                   (unsigned long long)n2, (unsigned long long)first.gi.ostride, (unsigned)(mix_in ? l_a / 2 : l_a), (unsigned)te->box_a) ||
         !encode_3d(&map_w, mid, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, wrows,
-                   (unsigned long long)n1, (unsigned long long)n, (unsigned)l_b, (unsigned)te->box_b) ||
+                   (unsigned long long)n1, (unsigned long long)n, (unsigned)(unmix_out ? l_b / 2 : l_b), (unsigned)te->box_b) ||
         !encode_3d(&map_out, dst, sizeof(V), (unsigned long long)n1, (unsigned long long)n2, (unsigned long long)rows,
-                   (unsigned long long)n1, (unsigned long long)dst_row_stride, (unsigned)l_b, (unsigned)te->box_b))
+                   (unsigned long long)n1, (unsigned long long)dst_row_stride, (unsigned)(unmix_out ? l_b / 2 : l_b), (unsigned)te->box_b))
         return 1;
     TmaArgs a{};
     a.work = mid;
@@ -395,11 +414,19 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     a.keep_out = keep_out;
     static const bool no_discard = [] { const char *e = getenv("DSC_TMA_NO_DISCARD"); return e != nullptr && *e == '1'; }();
     a.discard_work = !no_discard;
+    if (rf != nullptr) {
+        a.twr_lo = p->tw_real_lo; a.twr_hi = p->tw_real_hi;
+        a.real_shift = p->real_shift; a.real_mask = (1 << p->real_shift) - 1;
+        a.filt = rf->filt;
+        a.out = dst; a.out_pitch = dst_row_stride;
+        a.in = first.x; a.in_pitch = first.gi.ostride;
+    }
     const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
     if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
     const long long tiles = rows * (tiles_a + tiles_b);
     const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
-    if (e16) te->fn16<<<blocks, TMA_THREADS, te->smem16, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    if (rf != nullptr) te->fn_real<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    else if (e16) te->fn16<<<blocks, TMA_THREADS, te->smem16, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
     else te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
     return check_launch("four_step_tma");
 }
@@ -511,7 +538,8 @@ int cluster_launch(const dsc_cuda_plan *p, const void *x, long long x_row_stride
 // fused kernel does not cover fall back to two launches per chunk of rows.
 template <typename T, bool FWD>
 int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work, size_t work_bytes,
-              void *dst, long long dst_row_stride, bool scale, void *stream, bool keep_out = false) {
+              void *dst, long long dst_row_stride, bool scale, void *stream, bool keep_out = false,
+              const RealFuse *rf = nullptr) {
     using V = cx<T>;
     const long long n = p->n, n1 = 1LL << p->lg_n1, n2 = 1LL << p->lg_n2;
     const size_t row_bytes = (size_t)n * sizeof(V);
@@ -524,6 +552,12 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         first.in_limit = n;
     }
 
+#if !defined(DSC_EMUL)
+    // with the packed-real bin-pair step fused in: the TMA-fed launch or nothing (1 = not covered, the caller sweeps)
+    if (rf != nullptr) return four_step_tma_launch<T, FWD>(p, first, rows, work, work_bytes, dst, dst_row_stride, scale, stream, keep_out, rf);
+#else
+    if (rf != nullptr) return 1;
+#endif
 #if !defined(DSC_EMUL)
     {
         // dense complex rows up to 2^17 points: one line per thread-block cluster, the transpose through distributed
@@ -846,7 +880,11 @@ int run_rfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer, 
         FftArgs ac = a;
         ac.x = (const T *)x + (size_t)r0 * x_n;
         V *oc = (V *)out + (size_t)r0 * (n + 1);
-        int rc = four_step<T, true>(p, ac, rows, work, work_bytes, oc, n + 1, false, stream, true);
+        // un-mixing inside the transform's second pass (dense aligned rows): the spectrum is written once, as X
+        const RealFuse rf{nullptr};
+        int rc = take == 2 * n ? four_step<T, true>(p, ac, rows, work, work_bytes, oc, n + 1, false, stream, false, &rf) : 1;
+        if (rc <= 0) { if (rc) return rc; continue; }
+        rc = four_step<T, true>(p, ac, rows, work, work_bytes, oc, n + 1, false, stream, true);
         if (rc) return rc;
         const long long items = rows * (n / 2);
         const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
@@ -888,6 +926,17 @@ int run_irfft(const dsc_cuda_plan *p, const void *x, void *out, long long outer,
         return launch_lines(get_table<T, false, MODE_C2R, false>(), p->lg_n, a, stream, sizeof(T));
     }
     if (inner != 1) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass irfft (order %lld) along a strided axis", n);
+    if (take == n + 1) {
+        // the packed points are built inside the inverse transform's first pass (dense aligned bin rows): no packed rows
+        const RealFuse rf{nullptr};
+        FftArgs a{};
+        a.x = x;
+        a.gi = LineGeom{(long long)x_n, 1, 1LL << p->lg_n2};
+        a.in_limit = take;
+        a.in_kind = IN_COMPLEX;
+        const int rc = four_step<T, false>(p, a, outer, work, work_bytes, out, n, true, stream, false, &rf);
+        if (rc <= 0) return rc;
+    }
     // work = [ packed z rows of the chunk | four-step work ]
     const size_t row_bytes = (size_t)n * sizeof(V);
     if (!work || work_bytes < 2 * row_bytes + 4096) return fail(DSC_CUDA_ENOMEM, "work buffer holds no line (order %lld)", n);
@@ -959,15 +1008,21 @@ int run_filter(const dsc_cuda_plan *p, const void *x, const void *spectrum, void
         a.gi_pstride = 1;
         a.in_limit = take;
         a.in_kind = IN_PAIRS;
-        int rc = four_step<T, true>(p, a, rows, fs_work, fs_bytes, z, n, false, stream, true);
-        if (rc) return rc;
-        const long long items = rows * (n / 2);
-        const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
-        auto pk = filter_pairs_rows<T>;
-        DSC_LAUNCH(pk, blocks, 256, 0, stream, z, (const V *)spectrum, rows, (int)n,
-                   (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift, (1 << p->real_shift) - 1);
-        rc = check_launch("filter_pairs_rows");
-        if (rc) return rc;
+        // un-mix, spectrum product and mix inside the forward transform's second pass where the shape allows
+        const RealFuse rf{spectrum};
+        int rc = take == 2 * n ? four_step<T, true>(p, a, rows, fs_work, fs_bytes, z, n, false, stream, true, &rf) : 1;
+        if (rc < 0) return rc;
+        if (rc > 0) {
+            rc = four_step<T, true>(p, a, rows, fs_work, fs_bytes, z, n, false, stream, true);
+            if (rc) return rc;
+            const long long items = rows * (n / 2);
+            const int blocks = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+            auto pk = filter_pairs_rows<T>;
+            DSC_LAUNCH(pk, blocks, 256, 0, stream, z, (const V *)spectrum, rows, (int)n,
+                       (const V *)p->tw_real_lo, (const V *)p->tw_real_hi, p->real_shift, (1 << p->real_shift) - 1);
+            rc = check_launch("filter_pairs_rows");
+            if (rc) return rc;
+        }
         FftArgs b{};
         b.x = z;
         b.gi = LineGeom{n, 1, 1LL << p->lg_n2};

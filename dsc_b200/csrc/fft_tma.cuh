@@ -148,6 +148,14 @@ struct TmaArgs {
     int do_scale;
     int keep_out;                  // the output is re-read soon by another kernel: keep it in L2
     int discard_work;              // second-pass tiles drop their work-row lines from L2 once loaded (no write-back)
+    // fused packed-real launches (REAL != 0): bin-pair step inside the pass that holds both bins of a pair
+    const void *twr_lo, *twr_hi;   // W_2n^k split tables, k <= n/2
+    int real_shift, real_mask;
+    const void *filt;              // REAL == 1: spectrum B[0..n] of the fused filter (nullptr: plain rfft un-mix)
+    void *out;                     // REAL == 1: the output rows (for the two bins / the line no box store covers)
+    long long out_pitch;           // elements
+    const void *in;                // REAL == 2: the bin rows X[0..n] (for the one column no box load covers)
+    long long in_pitch;
 };
 
 struct TmaTileDesc { unsigned role_a, row, r, exit; };
@@ -175,9 +183,20 @@ template <typename T> DSC_DEV cx<T> tma_twiddle(const TmaArgs &a, const unsigned
 }
 
 // ---- one tile on one consumer group -----------------------------------------------------------------------
-template <typename T, int LG_N, int L, bool FWD, bool TRANSPOSE, int LGE = tma_lg_e<T>()>
+// SPLIT  : the tile's lines are two runs of L/2 adjacent lines, delivered (and stored) as two boxes [position][L/2],
+//          the second one behind the first (fused packed-real launches: a run and its mirror image).
+// PERMUTE: a TRANSPOSE tile writes its lines with the columns k1 > N/2 moved down by one and k1 = N/2 in the last column,
+//          so that the mirror image of an ALIGNED run of columns [a, a + m) of the next pass is the aligned run
+//          [N - a - m, N - a) (columns k1 = N - a - m + 1 .. N - a, where "N" stands for N/2).
+template <typename T, int LG_N, int L, bool FWD, bool TRANSPOSE, int LGE = tma_lg_e<T>(), bool SPLIT = false, bool PERMUTE = false>
 struct TmaTile {
     using V = cx<T>;
+    static constexpr int LH = L / 2;
+    // element index of (position, line) in the layout the boxes have
+    static DSC_DEV int box_at(const int pos, const int l) {
+        if constexpr (SPLIT) return (l >= LH ? (LH << LG_N) : 0) + pos * LH + (l & (LH - 1));
+        else return pos * L + l;
+    }
     static constexpr int LG_E = LGE < LG_N ? LGE : LG_N;
     using Sc = Sched<LG_N, LG_E>;
     static constexpr int N = Sc::N, E = Sc::E, TT = Sc::TT, STAGES = Sc::STAGES;
@@ -288,20 +307,33 @@ struct TmaTile {
         }
     }
 
+    // Column q of line ll of first-pass tile u.  SPLIT (fused irfft): the lo run [u LH, u LH + LH) and its mirror image
+    // [n2 - u LH - LH + 1, n2 - u LH]; column "n2" (tile 0) is the self-paired column n2/2.
+    static DSC_DEV unsigned line_q(const unsigned u, const unsigned ll, const unsigned n_other) {
+        if constexpr (SPLIT) {
+            if (ll < (unsigned)LH) return u * LH + ll;
+            const unsigned q = n_other - u * LH - LH + 1 + (ll - LH);
+            return q == n_other ? n_other / 2 : q;
+        } else {
+            (void)n_other;
+            return u * L + ll;
+        }
+    }
+
     // buf: the tile as the box delivered it, [position][line]; on return the finished tile, [line][position]
     // (TRANSPOSE, times the inter-pass twiddle W_n^(q k1)) or [position][line] (times the inverse's 1/n).
     // Inter-pass twiddles of a TRANSPOSE tile, W_n^(q k1) with k1 = j + c TT: W^(q j) per thread (returned) and W^(q TT c)
     // in a (c, line) table of the tile.  Depends on the tile's position only, so the launch calls it as soon as the tile's
     // descriptor is known, while the tile itself is still travelling.  The group barrier keeps the previous tile's readers
     // of the table ahead of its new contents.
-    static DSC_DEV V prepare(V *table, const TmaArgs &a, const unsigned q0, const int gtid, const int bar_id) {
+    static DSC_DEV V prepare(V *table, const TmaArgs &a, const unsigned u, const unsigned n_other, const int gtid, const int bar_id) {
         const int l_last = gtid / TT, j_last = gtid % TT;
         dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
         for (int i = gtid; i < L * E; i += TMA_GROUP_THREADS) {
             const unsigned ll = (unsigned)(i % L), c = (unsigned)(i / L);
-            table[i] = tma_twiddle<T>(a, (q0 + ll) * (unsigned)TT * c);
+            table[i] = tma_twiddle<T>(a, line_q(u, ll, n_other) * (unsigned)TT * c);
         }
-        return tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
+        return tma_twiddle<T>(a, line_q(u, (unsigned)l_last, n_other) * (unsigned)j_last);
     }
 
     static DSC_DEV void run(V *buf, V *table, const TmaArgs &a, const void *const *tw_all, const unsigned q0,
@@ -311,7 +343,7 @@ struct TmaTile {
         const int l_last = TRANSPOSE ? gtid / TT : l, j_last = TRANSPOSE ? gtid % TT : j;
         V v[E];
 #pragma unroll
-        for (int c = 0; c < E; ++c) v[c] = buf[(j + c * TT) * L + l];
+        for (int c = 0; c < E; ++c) v[c] = buf[box_at(j + c * TT, l)];
         if constexpr (TRANSPOSE) {
             if (!prepared) w0 = tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
         }
@@ -322,7 +354,9 @@ struct TmaTile {
 #pragma unroll
             for (int c = 0; c < E; ++c) {
                 const V w = c == 0 ? w0 : cmul(w0, table[c * L + l_last]);
-                buf[l_last * N + j_last + c * TT] = cmul_tw<FWD>(v[c], w);
+                const int k1 = j_last + c * TT;
+                const int col = !PERMUTE ? k1 : k1 < N / 2 ? k1 : k1 == N / 2 ? N - 1 : k1 - 1;
+                buf[l_last * N + col] = cmul_tw<FWD>(v[c], w);
             }
         } else {
             if (a.do_scale) {
@@ -331,7 +365,7 @@ struct TmaTile {
                 for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
             }
 #pragma unroll
-            for (int c = 0; c < E; ++c) buf[(j + c * TT) * L + l] = v[c];
+            for (int c = 0; c < E; ++c) buf[box_at(j + c * TT, l)] = v[c];
         }
     }
 
@@ -364,6 +398,129 @@ struct TmaTile {
     }
 };
 
+// ---- fused packed-real transforms: the bin-pair step on a finished second-pass tile ------------------------------
+// REAL == 1 (rfft and the forward half of the fused filter).  Pass A wrote its work lines with permuted columns
+// (TmaTile PERMUTE), so second-pass tile u holds two ALIGNED runs of LH = L/2 work columns:
+//   lo: columns [u LH, u LH + LH)           = k1 = u LH + l,                      l = 0 .. LH-1
+//   hi: columns [n1 - u LH - LH, n1 - u LH) = k1 = n1 - u LH - LH + 1 + m,        m = 0 .. LH-1   (k1 = "n1" is n1/2)
+// and bin k = k1 + n1 k2 of lo line l meets its partner n - k = (n1 - k1) + n1 (n2 - 1 - k2) in hi line LH-1-l at position
+// n2 - 1 - k2: both bins of every pair are in the tile, which leaves as X (or as the filter's packed z') instead of Z -- no
+// separate sweep over the spectrum (dsc_fft.h:199-214; real_mix_rows / filter_pairs_rows do the same per bin pair).  The
+// two self-paired lines share tile 0's pair (lo 0, hi LH-1): k1 = 0 pairs k2 with n2 - k2 (k2 = 0: DC and Nyquist, k2 = n2/2:
+// bin n/2), k1 = n1/2 pairs k2 with n2 - 1 - k2.  The hi run is stored one column further right than it was loaded
+// (k1 = column + 1); its last column in tile 0 falls outside the box store's tensor and is written by the group itself.
+// (The shifted box starts 16 bytes off an aligned run for complex128 -- fine -- but 8 bytes off for complex64, which the
+// bulk tensor store does not take: measured, the launch dies with "illegal instruction".)
+template <typename T, int LG_N1, int LG_N2, int L>
+DSC_DEV void tma_unmix_tile(cx<T> *buf, const TmaArgs &a, const unsigned u, const unsigned row, const int gtid, const int bar_id) {
+    using V = cx<T>;
+    constexpr int N2 = 1 << LG_N2, LH = L / 2;
+    constexpr unsigned n1 = 1u << LG_N1, n = 1u << (LG_N1 + LG_N2);
+    V *lo = buf, *hi = buf + N2 * LH;
+    const V *__restrict__ t_lo = (const V *)a.twr_lo, *__restrict__ t_hi = (const V *)a.twr_hi;
+    const V *__restrict__ flt = (const V *)a.filt;
+    // *pa = Z[k], *pb = Z[n - k] -> X[k], X[n - k] (or z'[k], z'[n - k]); the tables and the reference order want k <= n/2
+    auto pair = [&](V *pa, V *pb, const unsigned k) {
+        const bool up = k > n / 2;
+        const unsigned ks = up ? n - k : k;
+        const V w = cmul(__ldg(t_lo + (ks & (unsigned)a.real_mask)), __ldg(t_hi + (ks >> a.real_shift)));
+        const V za = up ? *pb : *pa, zb = up ? *pa : *pb;
+        V ra, rb;
+        if (flt != nullptr) filter_pair<T>(za, zb, w, __ldg(flt + ks), __ldg(flt + (n - ks)), ra, rb);
+        else real_pair<true, T>(za, zb, w, ra, rb);
+        *pa = up ? rb : ra;
+        *pb = up ? ra : rb;
+    };
+    dsc_group_barrier(bar_id, TMA_GROUP_THREADS);            // the finished tile is complete
+#pragma unroll 4
+    for (int i = gtid; i < N2 * LH; i += TMA_GROUP_THREADS) {
+        const int l = i % LH, k2 = i / LH;
+        if (u != 0 || l != 0) {
+            const unsigned k = (u * LH + l) + ((unsigned)k2 << LG_N1);
+            pair(lo + k2 * LH + l, hi + (N2 - 1 - k2) * LH + (LH - 1 - l), k);
+        } else if (k2 >= N2 / 2) {
+            const int kk = k2 - N2 / 2;                       // line k1 = n1/2
+            pair(hi + kk * LH + (LH - 1), hi + (N2 - 1 - kk) * LH + (LH - 1), n1 / 2 + ((unsigned)kk << LG_N1));
+        } else if (k2 != 0) {                                 // line k1 = 0
+            pair(lo + k2 * LH, lo + (N2 - k2) * LH, (unsigned)k2 << LG_N1);
+        } else {
+            const V z0 = lo[0], zh = lo[(N2 / 2) * LH];
+            if (flt != nullptr) {
+                lo[0] = filter_dc<T>(z0, __ldg(flt), __ldg(flt + n));
+                lo[(N2 / 2) * LH] = filter_mid<T>(zh, __ldg(flt + n / 2));
+            } else {
+                lo[0] = mk<T>(z0.x + z0.y, (T)0);
+                ((V *)a.out)[(long long)row * a.out_pitch + n] = mk<T>(z0.x - z0.y, (T)0);
+                lo[(N2 / 2) * LH] = mk<T>(zh.x, -zh.y);
+            }
+        }
+    }
+    if constexpr (sizeof(V) == 8) {
+        // complex64: the hi run's first column k1 = n1 - u LH - LH + 1 is odd, 8 bytes off the 16-byte granule a bulk tensor
+        // store must start on -- the group stores the run itself (rows of LH adjacent bins; k1 = "n1" is line n1/2)
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
+        V *o = (V *)a.out + (long long)row * a.out_pitch;
+        const unsigned k1_0 = n1 - u * LH - LH + 1;
+#pragma unroll 4
+        for (int i = gtid; i < N2 * LH; i += TMA_GROUP_THREADS) {
+            const unsigned k1 = k1_0 + (unsigned)(i % LH);
+            st_stream(o + (k1 == n1 ? n1 / 2 : k1) + ((long long)(i / LH) << LG_N1), hi[i]);
+        }
+    } else if (u == 0) {
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
+        V *o = (V *)a.out + (long long)row * a.out_pitch + n1 / 2;
+        for (int k2 = gtid; k2 < N2; k2 += TMA_GROUP_THREADS) o[(long long)k2 << LG_N1] = hi[k2 * LH + (LH - 1)];
+    }
+}
+
+// REAL == 2 (irfft): the packed points z[k] are built from the bin pairs (X[k], X[n - k]) inside the inverse transform's
+// FIRST pass.  With the bins viewed as [i1][q] (q < n2 + 1, row pitch n2: column n2 of row i1 is column 0 of row i1 + 1, and
+// bin n closes the last row), first-pass tile u loads two runs of LH = L/2 columns,
+//   lo: q = u LH + l,   hi: q = n2 - u LH - LH + 1 + m,     l, m = 0 .. LH-1,
+// and bin k = i1 n2 + q of lo line l meets n - k = (n1 - 1 - i1) n2 + (n2 - q) in hi line LH-1-l at row n1 - 1 - i1.  Tile 0's
+// hi line LH-1 (q = "n2") only serves as the partner of column 0; its slot is then given to the one column the runs leave
+// out, q = n2/2, whose bins the group fetched itself (xm: rows t and n1 - 1 - t per thread) while the boxes were travelling.
+template <typename T, int LG_N1, int LG_N2, int L>
+DSC_DEV void tma_mix_tile(cx<T> *buf, const TmaArgs &a, const unsigned u, const int gtid, const int bar_id,
+                          const cx<T> xm_a, const cx<T> xm_b) {
+    using V = cx<T>;
+    constexpr int N1 = 1 << LG_N1, LH = L / 2;
+    constexpr unsigned n2 = 1u << LG_N2, n = 1u << (LG_N1 + LG_N2);
+    V *lo = buf, *hi = buf + N1 * LH;
+    const V *__restrict__ t_lo = (const V *)a.twr_lo, *__restrict__ t_hi = (const V *)a.twr_hi;
+    // (X[k], X[n - k]) -> (z[k], z[n - k]); the tables and the reference order want k <= n/2
+    auto pair = [&](V xa, V xb, const unsigned k, V &za, V &zb) {
+        const bool up = k > n / 2;
+        const unsigned ks = up ? n - k : k;
+        const V w = cmul(__ldg(t_lo + (ks & (unsigned)a.real_mask)), __ldg(t_hi + (ks >> a.real_shift)));
+        if (ks == 0) { xa.y = (T)0; xb.y = (T)0; }            // imaginary parts of DC and Nyquist are ignored (dsc_fft.h:220-228)
+        V ra, rb;
+        real_pair<false, T>(up ? xb : xa, up ? xa : xb, w, ra, rb);
+        za = up ? rb : ra;
+        zb = up ? ra : rb;
+    };
+#pragma unroll 4
+    for (int i = gtid; i < N1 * LH; i += TMA_GROUP_THREADS) {
+        const int l = i % LH, i1 = i / LH;
+        V *pa = lo + i1 * LH + l, *pb = hi + (N1 - 1 - i1) * LH + (LH - 1 - l);
+        V za, zb;
+        pair(*pa, *pb, (unsigned)i1 * n2 + u * LH + l, za, zb);
+        *pa = za;
+        if (u != 0 || l != 0) *pb = zb;
+    }
+    if (u == 0) {
+        // column n2/2 into the slot of hi line LH-1: rows t and N1 - 1 - t are a pair
+        dsc_group_barrier(bar_id, TMA_GROUP_THREADS);        // the partners of column 0 have been read
+        for (int t = gtid; t < N1 / 2; t += TMA_GROUP_THREADS) {
+            V za, zb;
+            pair(xm_a, xm_b, (unsigned)t * n2 + n2 / 2, za, zb);
+            hi[t * LH + (LH - 1)] = za;
+            hi[(N1 - 1 - t) * LH + (LH - 1)] = zb;
+        }
+    }
+    dsc_group_barrier(bar_id, TMA_GROUP_THREADS);            // the tile holds z
+}
+
 // ---- the persistent launch --------------------------------------------------------------------------------
 // One block per SM: warps 0..15 are two butterfly groups, lane 0 of warp 16 is the loader, lane 0 of warp 17 the
 // storer.  The block's tile sequence is t = 0, 1, 2, ...: tile t is transformed by group t % 2 in buffer t % 3.
@@ -381,7 +538,9 @@ struct TmaTile {
 // warps, but two 512-thread groups plus the copy warps exceed the 1024-thread block limit; so the 16-point variant runs on
 // 32 KiB tiles (groups stay 256 threads) with TWO blocks per SM: 32 butterfly warps, six tiles in flight.  It covers float
 // passes of up to 512 points (32-byte rows beyond that).
-template <typename T, int LG_N1, int LG_N2, bool FWD, int LGE = tma_lg_e<T>(), int TILE = TMA_TILE_BYTES>
+// REAL: 0 = complex rows; 1 = forward with the packed-real bin-pair step fused into the second pass (tma_unmix_tile);
+// 2 = inverse whose first pass builds the packed points from the bins of the real transform (tma_mix_tile).
+template <typename T, int LG_N1, int LG_N2, bool FWD, int LGE = tma_lg_e<T>(), int TILE = TMA_TILE_BYTES, int REAL = 0>
 __global__ void __launch_bounds__(TMA_THREADS, (TILE * 2 <= TMA_TILE_BYTES ? 2 : 1))
 four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const __grid_constant__ CUtensorMap map_out, const TmaArgs a, const FourStepSync s) {
@@ -389,8 +548,13 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     constexpr int TMA_TILE_BYTES = TILE;           // shadows the default for everything below
     constexpr int L_A = (TILE / (int)sizeof(V)) >> LG_N1, L_B = (TILE / (int)sizeof(V)) >> LG_N2;
     constexpr int BOX_A = tma_box_rows(LG_N1), BOX_B = tma_box_rows(LG_N2);
-    using TileA = TmaTile<T, LG_N1, L_A, FWD, true, LGE>;
-    using TileB = TmaTile<T, LG_N2, L_B, FWD, false, LGE>;
+    using TileA = TmaTile<T, LG_N1, L_A, FWD, true, LGE, REAL == 2, REAL == 1>;
+    using TileB = TmaTile<T, LG_N2, L_B, FWD, false, LGE, REAL == 1>;
+    constexpr int LH_B = L_B / 2;                  // REAL == 1: second-pass tiles are two runs of LH_B work columns
+    constexpr int LH_A = L_A / 2;                  // REAL == 2: first-pass tiles are two runs of LH_A bin columns
+    static_assert(REAL != 1 || (FWD && LH_B * (int)sizeof(V) >= 64), "fused packed-real tiles: runs of at least 64 bytes");
+    static_assert(REAL != 2 || (!FWD && LH_A * (int)sizeof(V) >= 64 && (1 << LG_N1) / 2 <= TMA_GROUP_THREADS),
+                  "fused packed-real tiles: runs of at least 64 bytes, one pair of the middle column per thread");
     using Smem = TmaSmem<T, TILE>;
     static_assert(L_A * TileA::E <= Smem::TABLE_MAX, "inter-pass table");
     DSC_DYN_SMEM(smem_raw);
@@ -469,14 +633,31 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 if (role_a) {
                     constexpr int ROWS = 1 << LG_N1;
 #pragma unroll
-                    for (int r0 = 0; r0 < ROWS; r0 += BOX_A)
-                        tma::load_3d(sm.buf[b] + (size_t)r0 * L_A * sizeof(V), &map_x, (int)r * L_A * ES, r0, (int)row, &sm.full[b], pol_stream);
+                    for (int r0 = 0; r0 < ROWS; r0 += BOX_A) {
+                        if constexpr (REAL == 2) {
+                            // map_x has n2 + 1 columns at a row pitch of n2: the mirror image of columns [0, LH) ends in column n2
+                            tma::load_3d(sm.buf[b] + (size_t)r0 * LH_A * sizeof(V), &map_x, (int)r * LH_A * ES, r0, (int)row,
+                                         &sm.full[b], pol_stream);
+                            tma::load_3d(sm.buf[b] + (size_t)(ROWS + r0) * LH_A * sizeof(V), &map_x,
+                                         ((1 << LG_N2) - (int)r * LH_A - LH_A + 1) * ES, r0, (int)row, &sm.full[b], pol_stream);
+                        } else {
+                            tma::load_3d(sm.buf[b] + (size_t)r0 * L_A * sizeof(V), &map_x, (int)r * L_A * ES, r0, (int)row, &sm.full[b], pol_stream);
+                        }
+                    }
                 } else {
                     const long long wrow = a.ring ? row % a.ring : row;
                     constexpr int ROWS = 1 << LG_N2;
 #pragma unroll
-                    for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
-                        tma::load_3d(sm.buf[b] + (size_t)r0 * L_B * sizeof(V), &map_w, (int)r * L_B * ES, r0, (int)wrow, &sm.full[b], pol_stream);
+                    for (int r0 = 0; r0 < ROWS; r0 += BOX_B) {
+                        if constexpr (REAL == 1) {
+                            tma::load_3d(sm.buf[b] + (size_t)r0 * LH_B * sizeof(V), &map_w, (int)r * LH_B * ES, r0, (int)wrow,
+                                         &sm.full[b], pol_stream);
+                            tma::load_3d(sm.buf[b] + (size_t)(ROWS + r0) * LH_B * sizeof(V), &map_w,
+                                         ((1 << LG_N1) - (int)r * LH_B - LH_B) * ES, r0, (int)wrow, &sm.full[b], pol_stream);
+                        } else {
+                            tma::load_3d(sm.buf[b] + (size_t)r0 * L_B * sizeof(V), &map_w, (int)r * L_B * ES, r0, (int)wrow, &sm.full[b], pol_stream);
+                        }
+                    }
                 }
             }
         } else {
@@ -510,14 +691,37 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 if (d.role_a) {
                     // L_A contiguous lines W[q0 + l][k1] of the work row
                     const long long wrow = a.ring ? d.row % a.ring : d.row;
+                    if constexpr (REAL == 2) {
+                        // the two runs of work lines W[q][k1] (TmaTile::line_q); tile 0's last line is q = n2/2
+                        V *wr = (V *)a.work + ((wrow << LG_N2) << LG_N1);
+                        constexpr unsigned LINE = (unsigned)sizeof(V) << LG_N1;
+                        const long long q_hi = (1 << LG_N2) - (long long)d.r * LH_A - LH_A + 1;
+                        tma::store_linear(wr + ((long long)d.r * LH_A << LG_N1), sm.buf[b], LH_A * LINE, pol_keep);
+                        if (d.r != 0) tma::store_linear(wr + (q_hi << LG_N1), sm.buf[b] + LH_A * LINE, LH_A * LINE, pol_keep);
+                        else {
+                            tma::store_linear(wr + (q_hi << LG_N1), sm.buf[b] + LH_A * LINE, (LH_A - 1) * LINE, pol_keep);
+                            tma::store_linear(wr + ((long long)(1 << LG_N2) / 2 << LG_N1), sm.buf[b] + (2 * LH_A - 1) * LINE, LINE, pol_keep);
+                        }
+                    } else {
                     V *dst = (V *)a.work + ((wrow << LG_N2) + (long long)d.r * L_A << LG_N1);
                     tma::store_linear(dst, sm.buf[b], TMA_TILE_BYTES, pol_keep);
+                    }
                 } else {
                     constexpr int ROWS = 1 << LG_N2;
 #pragma unroll
-                    for (int r0 = 0; r0 < ROWS; r0 += BOX_B)
-                        tma::store_3d(&map_out, (int)d.r * L_B * ES, r0, (int)d.row, sm.buf[b] + (size_t)r0 * L_B * sizeof(V),
-                                      a.keep_out ? pol_keep : pol_stream);
+                    for (int r0 = 0; r0 < ROWS; r0 += BOX_B) {
+                        if constexpr (REAL == 1) {
+                            // the hi run holds k1 = column + 1 (TmaTile PERMUTE); k1 = n1 (tile 0) is clipped by the tensor
+                            tma::store_3d(&map_out, (int)d.r * LH_B * ES, r0, (int)d.row, sm.buf[b] + (size_t)r0 * LH_B * sizeof(V),
+                                          a.keep_out ? pol_keep : pol_stream);
+                            if constexpr (sizeof(V) == 16)       // complex64: stored by the group (tma_unmix_tile)
+                                tma::store_3d(&map_out, ((1 << LG_N1) - (int)d.r * LH_B - LH_B + 1) * ES, r0, (int)d.row,
+                                              sm.buf[b] + (size_t)(ROWS + r0) * LH_B * sizeof(V), a.keep_out ? pol_keep : pol_stream);
+                        } else {
+                            tma::store_3d(&map_out, (int)d.r * L_B * ES, r0, (int)d.row, sm.buf[b] + (size_t)r0 * L_B * sizeof(V),
+                                          a.keep_out ? pol_keep : pol_stream);
+                        }
+                    }
                 }
                 tma::store_commit();
                 tma::store_wait_read();
@@ -540,27 +744,47 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         tma::mbar_wait(&sm.posted[b], (t / TMA_BUFFERS) & 1, "group: posted");
         const TmaTileDesc d = sm.desc[b];
         V w0 = mk<T>((T)1, (T)0);
-        if (d.role_a && !d.exit) w0 = TileA::prepare(sm.table[group], a, d.r * (unsigned)L_A, gtid, bar_id);
+        if (d.role_a && !d.exit) w0 = TileA::prepare(sm.table[group], a, d.r, 1u << LG_N2, gtid, bar_id);
+        V xm_a = V{}, xm_b = V{};
+        if constexpr (REAL == 2) {
+            // the bins of column n2/2 (tile 0 only), rows gtid and n1 - 1 - gtid: fetched while the boxes travel
+            if (d.role_a && !d.exit && d.r == 0 && gtid < (1 << LG_N1) / 2) {
+                const V *xr = (const V *)a.in + (long long)d.row * a.in_pitch + (1 << LG_N2) / 2;
+                xm_a = __ldg(xr + ((long long)gtid << LG_N2));
+                xm_b = __ldg(xr + ((long long)((1 << LG_N1) - 1 - gtid) << LG_N2));
+            }
+        }
         tma::mbar_wait(&sm.full[b], (t / TMA_BUFFERS) & 1, "group: full");
         if (d.exit) { tma::mbar_arrive(&sm.ready[b]); break; }
         V *buf = reinterpret_cast<V *>(sm.buf[b]);
+        if constexpr (REAL == 2) {
+            if (d.role_a) tma_mix_tile<T, LG_N1, LG_N2, L_A>(buf, a, d.r, gtid, bar_id, xm_a, xm_b);
+        }
         if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id, sm.ladder[0], true, w0);
         else {
-            if constexpr (L_B * (int)sizeof(V) >= 128) {
-                // The work-row box this tile was loaded from is dead now: nobody else reads these lines, and the slot is
+            constexpr int RUNS = REAL == 1 ? 2 : 1, RUN_BYTES = (REAL == 1 ? LH_B : L_B) * (int)sizeof(V);
+            if constexpr (RUN_BYTES >= 128) {
+                // The work-row box(es) this tile was loaded from are dead now: nobody else reads these lines, and the slot is
                 // only written again a ring turn later.  Drop the (dirty) lines from L2 instead of letting them be
                 // written back to HBM when they are evicted -- the ring write-back was 35 - 40 % of all DRAM writes.
                 if (a.discard_work) {
                     const long long wrow = a.ring ? d.row % a.ring : d.row;
-                    const char *base = (const char *)a.work + (((wrow << LG_N2) << LG_N1) + (long long)d.r * L_B) * (long long)sizeof(V);
-                    constexpr int PER_ROW = L_B * (int)sizeof(V) / 128, LINES = (1 << LG_N2) * PER_ROW;
-                    for (int i = gtid; i < LINES; i += TMA_GROUP_THREADS) {
-                        const char *p = base + (long long)(i / PER_ROW) * ((long long)sizeof(V) << LG_N1) + (i % PER_ROW) * 128;
-                        asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+                    const char *row0 = (const char *)a.work + ((wrow << LG_N2) << LG_N1) * (long long)sizeof(V);
+                    constexpr int PER_ROW = RUN_BYTES / 128, LINES = (1 << LG_N2) * PER_ROW;
+#pragma unroll
+                    for (int run = 0; run < RUNS; ++run) {
+                        const long long col = REAL == 1 ? (run == 0 ? (long long)d.r * LH_B : (1 << LG_N1) - (long long)d.r * LH_B - LH_B)
+                                                        : (long long)d.r * L_B;
+                        const char *base = row0 + col * (long long)sizeof(V);
+                        for (int i = gtid; i < LINES; i += TMA_GROUP_THREADS) {
+                            const char *p = base + (long long)(i / PER_ROW) * ((long long)sizeof(V) << LG_N1) + (i % PER_ROW) * 128;
+                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+                        }
                     }
                 }
             }
             TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id, sm.ladder[1]);
+            if constexpr (REAL == 1) tma_unmix_tile<T, LG_N1, LG_N2, L_B>(buf, a, d.r, d.row, gtid, bar_id);
         }
         tma::fence_async_smem();
         tma::mbar_arrive(&sm.ready[b]);
