@@ -318,6 +318,15 @@ inline bool real_fuse_disabled() {
     static const bool off = [] { const char *e = getenv("DSC_NO_REAL_FUSE"); return e != nullptr && *e != '\0' && *e != '0'; }();
     return off;
 }
+// float32 filter: the fused forward launch is parity-green but measures 3 - 5 % SLOWER than transform + bin-pair sweep on
+// B200 (1.91 - 1.99 ms against 1.83 - 1.87 ms per GiB at 2^16 .. 2^20 samples): complex64 runs start 8 bytes off the 16-byte
+// granule of a bulk tensor store, so half of every tile leaves through the group's own stores, and the pair step (two
+// un-mix/mix steps, two spectrum bins per pair) doubles the instructions of a second-pass tile in a launch that is paced by
+// its instruction stream.  float64 gains 33 % (rfft) / 65 % (irfft).  Opt-in for float32: DSC_REAL_FUSE_F32=1 (tests do).
+inline bool real_fuse_f32() {
+    static const bool on = [] { const char *e = getenv("DSC_REAL_FUSE_F32"); return e != nullptr && *e == '1'; }();
+    return on;
+}
 
 // Returns 1 when the shape is not covered (the caller continues with four_step_fused), 0 on success, < 0 on error.
 template <typename T, bool FWD>
@@ -329,6 +338,8 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     TmaEntry *te = tma_entry<T, FWD>(p->lg_n1, p->lg_n2);
     if (te == nullptr || tma_disabled()) return 1;
     if (rf != nullptr && (te->fn_real == nullptr || real_fuse_disabled() || p->tw_real_lo == nullptr ||
+                          (sizeof(T) == 4 && !real_fuse_f32()) ||
+                          p->real_shift > p->lg_n2 || p->real_shift > p->lg_n1 ||
                           (FWD ? dst_row_stride < n + (rf->filt ? 0 : 1) : (first.in_limit < n + 1 || first.gi.ostride < n + 1))))
         return 1;
     // 16 points per thread on 32 KiB tiles, two blocks per SM (twice the butterfly warps), where the plan carries its tables.
@@ -436,6 +447,14 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
 // (TMA-fed two-pass launch: 3.0), 2.46 at 2^16 (2.98), 1.97 at 2^17 (2.80), 3.85 at 2^14 (single-pass block: 4.30).
 // Default: 2^15 only.  DSC_CLUSTER_LGS=14,15,16,17 selects others (tests do), DSC_NO_CLUSTER=1 none; DSC_CLUSTER_PIPE=0
 // selects the one-line-per-cluster launch instead of the persistent pipelined one.
+// No DSC_CLUSTER_LGS / DSC_NO_CLUSTER in the environment: 2^15-point batches are decided per device by measurement.
+inline bool cluster_autotuned() {
+    static const bool on = [] {
+        const char *off = getenv("DSC_NO_CLUSTER"), *e = getenv("DSC_CLUSTER_LGS");
+        return !(off != nullptr && *off != '\0' && *off != '0') && (e == nullptr || *e == '\0');
+    }();
+    return on;
+}
 inline bool cluster_wanted(const int lg_n) {
     static const unsigned mask = [] {
         const char *off = getenv("DSC_NO_CLUSTER");
@@ -564,8 +583,38 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         // shared memory (fft_cluster.cuh); beyond that the TMA-fed two-pass launch (fft_tma.cuh)
         if (first.in_kind == IN_COMPLEX && first.in_limit >= n && first.seg_shift == 0 && first.gi.lstride == 1 &&
             first.gi.estride == n2 && first.ring_in == 0) {
-            const int rcc = cluster_launch<T, FWD>(p, first.x, first.gi.ostride, dst, dst_row_stride, rows, scale, stream);
-            if (rcc <= 0) return rcc;
+            // 2^15 points: which launch wins depends on the part -- how many clusters its GPCs co-schedule.  Measured on four
+            // B200s: pipelined clusters 3.27 / 3.28 / 2.84 / 2.87 TB/s, the TMA-fed two-pass launch 3.08 on each.  The first
+            // batch large enough to time (>= 2^24 points, out of place, not under stream capture) runs both twice -- repeating an
+            // out-of-place transform is harmless -- and the faster one serves the process from then on.
+            static int choice = 0;                  // per (T, FWD): 0 undecided, 1 clusters, 2 two-pass
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (choice == 0 && cluster_autotuned() && cluster_wanted(p->lg_n) && rows * n >= (1LL << 24) && first.x != dst &&
+                cudaStreamIsCapturing((cudaStream_t)stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+                cudaEvent_t ev[5];
+                for (auto &e : ev) cudaEventCreate(&e);
+                int rc_c = 0, rc_t = 0;
+                cudaEventRecord(ev[0], (cudaStream_t)stream);
+                for (int rep = 0; rep < 2 && rc_c == 0 && rc_t == 0; ++rep) {
+                    rc_c = cluster_launch<T, FWD>(p, first.x, first.gi.ostride, dst, dst_row_stride, rows, scale, stream);
+                    cudaEventRecord(ev[1 + 2 * rep], (cudaStream_t)stream);
+                    if (rc_c == 0) rc_t = four_step_tma_launch<T, FWD>(p, first, rows, work, work_bytes, dst, dst_row_stride, scale, stream, keep_out);
+                    cudaEventRecord(ev[2 + 2 * rep], (cudaStream_t)stream);
+                }
+                float t_c = 0.f, t_t = 0.f;
+                if (rc_c == 0 && rc_t == 0 && cudaEventSynchronize(ev[4]) == cudaSuccess &&
+                    cudaEventElapsedTime(&t_c, ev[2], ev[3]) == cudaSuccess && cudaEventElapsedTime(&t_t, ev[3], ev[4]) == cudaSuccess)
+                    choice = t_c <= t_t ? 1 : 2;
+                for (auto &e : ev) cudaEventDestroy(e);
+                if (rc_c < 0 || rc_t < 0) return rc_c < 0 ? rc_c : rc_t;
+                if (choice != 0) return 0;          // dst holds the transform (written by the last launch)
+                cudaGetLastError();
+                choice = rc_c > 0 ? 2 : 1;          // one of them does not cover the shape: nothing to decide
+            }
+            if (!(choice == 2 && cluster_autotuned())) {
+                const int rcc = cluster_launch<T, FWD>(p, first.x, first.gi.ostride, dst, dst_row_stride, rows, scale, stream);
+                if (rcc <= 0) return rcc;
+            }
         }
         const int rc = four_step_tma_launch<T, FWD>(p, first, rows, work, work_bytes, dst, dst_row_stride, scale, stream, keep_out);
         if (rc <= 0) return rc;

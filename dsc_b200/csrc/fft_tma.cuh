@@ -431,27 +431,72 @@ DSC_DEV void tma_unmix_tile(cx<T> *buf, const TmaArgs &a, const unsigned u, cons
         *pa = up ? rb : ra;
         *pb = up ? ra : rb;
     };
+    // A thread keeps its line l (the group's 256 threads are a multiple of LH) and takes every K2_STEP-th position:
+    // W_2n^k = W_2n^k1 (one lookup per tile) times W_2n^(n1 k2) (one entry of the coarse table per pair; the upper half by
+    // W^(n1 (n2 - m)) = -conj W^(n1 m)), valid for every 0 < k < n -- no role swap, one table load per pair.
+    constexpr int PAIRS = N2 * LH / TMA_GROUP_THREADS, K2_STEP = TMA_GROUP_THREADS / LH;
+    static_assert(PAIRS * TMA_GROUP_THREADS == N2 * LH && K2_STEP * LH == TMA_GROUP_THREADS, "whole pairs per thread");
+    const int l = gtid % LH, k2_0 = gtid / LH;
+    const bool special = u == 0 && l == 0;
+    const unsigned k1 = u * LH + l;
+    const int d = LG_N1 - a.real_shift;                      // coarse-table entries per step of n1 (log2)
+    constexpr int CH = PAIRS < 4 ? PAIRS : 4;                // spectrum bins are requested CH pairs at a time (L2 hits)
+    static_assert(PAIRS % CH == 0, "whole chunks");
+    V fa[CH], fb[CH];
+    V w1 = mk<T>((T)1, (T)0);
+    auto request = [&](const int p0) {
+#pragma unroll
+        for (int p = 0; p < CH; ++p) {
+            const unsigned k = k1 + ((unsigned)(k2_0 + (p0 + p) * K2_STEP) << LG_N1);
+            fa[p] = __ldg(flt + k);
+            fb[p] = __ldg(flt + (n - k));
+        }
+    };
+    if (!special) {
+        w1 = cmul(__ldg(t_lo + (k1 & (unsigned)a.real_mask)), __ldg(t_hi + (k1 >> a.real_shift)));
+        if (flt != nullptr) request(0);
+    }
     dsc_group_barrier(bar_id, TMA_GROUP_THREADS);            // the finished tile is complete
-#pragma unroll 4
-    for (int i = gtid; i < N2 * LH; i += TMA_GROUP_THREADS) {
-        const int l = i % LH, k2 = i / LH;
-        if (u != 0 || l != 0) {
-            const unsigned k = (u * LH + l) + ((unsigned)k2 << LG_N1);
-            pair(lo + k2 * LH + l, hi + (N2 - 1 - k2) * LH + (LH - 1 - l), k);
-        } else if (k2 >= N2 / 2) {
-            const int kk = k2 - N2 / 2;                       // line k1 = n1/2
-            pair(hi + kk * LH + (LH - 1), hi + (N2 - 1 - kk) * LH + (LH - 1), n1 / 2 + ((unsigned)kk << LG_N1));
-        } else if (k2 != 0) {                                 // line k1 = 0
-            pair(lo + k2 * LH, lo + (N2 - k2) * LH, (unsigned)k2 << LG_N1);
-        } else {
-            const V z0 = lo[0], zh = lo[(N2 / 2) * LH];
-            if (flt != nullptr) {
-                lo[0] = filter_dc<T>(z0, __ldg(flt), __ldg(flt + n));
-                lo[(N2 / 2) * LH] = filter_mid<T>(zh, __ldg(flt + n / 2));
+    if (!special) {
+#pragma unroll
+        for (int p0 = 0; p0 < PAIRS; p0 += CH) {
+            V ra[CH], rb[CH];
+#pragma unroll
+            for (int p = 0; p < CH; ++p) {
+                const int k2 = k2_0 + (p0 + p) * K2_STEP;
+                const bool up = k2 > N2 / 2;
+                const V wt = __ldg(t_hi + ((unsigned)(up ? N2 - k2 : k2) << d));
+                const V w = cmul(w1, up ? mk<T>(-wt.x, wt.y) : wt);
+                const V za = lo[k2 * LH + l], zb = hi[(N2 - 1 - k2) * LH + (LH - 1 - l)];
+                if (flt != nullptr) filter_pair<T>(za, zb, w, fa[p], fb[p], ra[p], rb[p]);
+                else real_pair<true, T>(za, zb, w, ra[p], rb[p]);
+            }
+            if (flt != nullptr && p0 + CH < PAIRS) request(p0 + CH);
+#pragma unroll
+            for (int p = 0; p < CH; ++p) {
+                const int k2 = k2_0 + (p0 + p) * K2_STEP;
+                lo[k2 * LH + l] = ra[p];
+                hi[(N2 - 1 - k2) * LH + (LH - 1 - l)] = rb[p];
+            }
+        }
+    } else {
+        // tile 0, the pair of self-paired lines (lo 0, hi LH-1)
+        for (int k2 = k2_0; k2 < N2; k2 += K2_STEP) {
+            if (k2 >= N2 / 2) {
+                const int kk = k2 - N2 / 2;                       // line k1 = n1/2
+                pair(hi + kk * LH + (LH - 1), hi + (N2 - 1 - kk) * LH + (LH - 1), n1 / 2 + ((unsigned)kk << LG_N1));
+            } else if (k2 != 0) {                                 // line k1 = 0
+                pair(lo + k2 * LH, lo + (N2 - k2) * LH, (unsigned)k2 << LG_N1);
             } else {
-                lo[0] = mk<T>(z0.x + z0.y, (T)0);
-                ((V *)a.out)[(long long)row * a.out_pitch + n] = mk<T>(z0.x - z0.y, (T)0);
-                lo[(N2 / 2) * LH] = mk<T>(zh.x, -zh.y);
+                const V z0 = lo[0], zh = lo[(N2 / 2) * LH];
+                if (flt != nullptr) {
+                    lo[0] = filter_dc<T>(z0, __ldg(flt), __ldg(flt + n));
+                    lo[(N2 / 2) * LH] = filter_mid<T>(zh, __ldg(flt + n / 2));
+                } else {
+                    lo[0] = mk<T>(z0.x + z0.y, (T)0);
+                    ((V *)a.out)[(long long)row * a.out_pitch + n] = mk<T>(z0.x - z0.y, (T)0);
+                    lo[(N2 / 2) * LH] = mk<T>(zh.x, -zh.y);
+                }
             }
         }
     }
@@ -499,14 +544,28 @@ DSC_DEV void tma_mix_tile(cx<T> *buf, const TmaArgs &a, const unsigned u, const 
         za = up ? rb : ra;
         zb = up ? ra : rb;
     };
-#pragma unroll 4
-    for (int i = gtid; i < N1 * LH; i += TMA_GROUP_THREADS) {
-        const int l = i % LH, i1 = i / LH;
-        V *pa = lo + i1 * LH + l, *pb = hi + (N1 - 1 - i1) * LH + (LH - 1 - l);
-        V za, zb;
-        pair(*pa, *pb, (unsigned)i1 * n2 + u * LH + l, za, zb);
-        *pa = za;
-        if (u != 0 || l != 0) *pb = zb;
+    // a thread keeps its column q = u LH + l and takes every I1_STEP-th row: W_2n^k = W_2n^q times W_2n^(n2 i1), as in
+    // tma_unmix_tile
+    constexpr int PAIRS = N1 * LH / TMA_GROUP_THREADS, I1_STEP = TMA_GROUP_THREADS / LH;
+    static_assert(PAIRS * TMA_GROUP_THREADS == N1 * LH && I1_STEP * LH == TMA_GROUP_THREADS, "whole pairs per thread");
+    {
+        const int l = gtid % LH, i1_0 = gtid / LH;
+        const unsigned q = u * LH + l;
+        const int d = LG_N2 - a.real_shift;
+        const V w1 = cmul(__ldg(t_lo + (q & (unsigned)a.real_mask)), __ldg(t_hi + (q >> a.real_shift)));
+#pragma unroll
+        for (int p = 0; p < PAIRS; ++p) {
+            const int i1 = i1_0 + p * I1_STEP;
+            const bool up = i1 > N1 / 2;
+            const V wt = __ldg(t_hi + ((unsigned)(up ? N1 - i1 : i1) << d));
+            const V w = cmul(w1, up ? mk<T>(-wt.x, wt.y) : wt);
+            V *pa = lo + i1 * LH + l, *pb = hi + (N1 - 1 - i1) * LH + (LH - 1 - l);
+            V xa = *pa, xb = *pb, za, zb;
+            if (q == 0 && i1 == 0) { xa.y = (T)0; xb.y = (T)0; }       // imaginary parts of DC and Nyquist are ignored (dsc_fft.h:220-228)
+            real_pair<false, T>(xa, xb, w, za, zb);
+            *pa = za;
+            if (q != 0) *pb = zb;                                      // tile 0: hi line LH-1 is only column 0's partner
+        }
     }
     if (u == 0) {
         // column n2/2 into the slot of hi line LH-1: rows t and N1 - 1 - t are a pair

@@ -4,6 +4,7 @@
    registers    the register-direct persistent launch (four_step_fused), no TMA, no clusters
    tma-e16      the TMA-fed launch with 16 points per thread on 32 KiB tiles, two blocks per SM (opt-in variant)
    real-sweep   packed-real transforms with the bin-pair step as a separate sweep instead of fused into the TMA-fed launch
+   real-fused-f32  the float32 filter through the fused launch too (default for float64 only: slower for float32)
 The selection is made through environment variables the library reads once, hence one subprocess per variant."""
 import os
 import subprocess
@@ -21,10 +22,11 @@ pytestmark = pytest.mark.gpu
                                       ("clusters-unpipelined", {"DSC_CLUSTER_LGS": "14,15,16,17", "DSC_CLUSTER_PIPE": "0"}),
                                       ("registers", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1"}),
                                       ("tma-e16", {"DSC_TMA_E16": "1", "DSC_NO_CLUSTER": "1"}),
-                                      ("real-sweep", {"DSC_NO_REAL_FUSE": "1"})])
+                                      ("real-sweep", {"DSC_NO_REAL_FUSE": "1"}),
+                                      ("real-fused-f32", {"DSC_REAL_FUSE_F32": "1"})])
 def test_two_pass_paths(name, env):
     e = dict(os.environ)
-    for k in ("DSC_NO_TMA", "DSC_NO_CLUSTER", "DSC_CLUSTER_LGS", "DSC_TMA_E16", "DSC_CLUSTER_PIPE", "DSC_NO_REAL_FUSE"):
+    for k in ("DSC_NO_TMA", "DSC_NO_CLUSTER", "DSC_CLUSTER_LGS", "DSC_TMA_E16", "DSC_CLUSTER_PIPE", "DSC_NO_REAL_FUSE", "DSC_REAL_FUSE_F32"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, WORKER], capture_output=True, text=True, timeout=600, env=e)
