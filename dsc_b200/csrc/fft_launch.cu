@@ -392,9 +392,9 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     s.ring = (int)ring;
     s.rows = (int)rows;
     {
-        // a tile is published about four tile times after its ticket was taken, while the whole GPU takes
+        // a tile is published about five tile times after its ticket was taken (two of them waiting in the loader), while the whole GPU takes
         // ~grid tickets per tile time: put a row's second pass that far behind its first pass
-        long long lag = (4LL * resident + tiles_b + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
+        long long lag = (5LL * resident + tiles_b + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
         if (lag < 1) lag = 1;
         if (ring > 0 && lag > ring / 2) lag = ring / 2;
         if (lag > rows) lag = rows;
@@ -425,6 +425,8 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     a.keep_out = keep_out;
     static const bool no_discard = [] { const char *e = getenv("DSC_TMA_NO_DISCARD"); return e != nullptr && *e == '1'; }();
     a.discard_work = !no_discard;
+    static const bool no_prefetch = [] { const char *e = getenv("DSC_TMA_PREFETCH"); return e != nullptr && *e == '0'; }();
+    a.prefetch = !no_prefetch;
     if (rf != nullptr) {
         a.twr_lo = p->tw_real_lo; a.twr_hi = p->tw_real_hi;
         a.real_shift = p->real_shift; a.real_mask = (1 << p->real_shift) - 1;

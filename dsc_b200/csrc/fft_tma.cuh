@@ -107,6 +107,10 @@ DSC_DEV void load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, 
         " [%0], [%1, {%2, %3, %4}], [%5], %6;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+// box -> L2 only: the later load of the same box finds it there
+DSC_DEV void prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 DSC_DEV void store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src, unsigned long long pol) {
     asm volatile(
         "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
@@ -126,7 +130,10 @@ DSC_DEV void store_wait_all_but_one() { asm volatile("cp.async.bulk.wait_group 1
 // ---- geometry of one launch -------------------------------------------------------------------------------
 constexpr int TMA_TILE_BYTES = 64 * 1024;
 constexpr int TMA_BUFFERS = 3;
-constexpr int TMA_GROUPS = 2;                 // consumer groups of TMA_GROUP_THREADS threads
+#if !defined(DSC_TMA_GROUPS)
+#define DSC_TMA_GROUPS 2
+#endif
+constexpr int TMA_GROUPS = DSC_TMA_GROUPS;                 // consumer groups of TMA_GROUP_THREADS threads
 constexpr int TMA_GROUP_THREADS = 256;
 constexpr int TMA_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 64;     // + the loader warp and the storer warp
 
@@ -156,6 +163,7 @@ struct TmaArgs {
     long long out_pitch;           // elements
     const void *in;                // REAL == 2: the bin rows X[0..n] (for the one column no box load covers)
     long long in_pitch;
+    int prefetch;                  // first-pass boxes are prefetched into L2 when their ticket is taken, two tiles ahead
 };
 
 struct TmaTileDesc { unsigned role_a, row, r, exit; };
@@ -644,7 +652,33 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         constexpr int ES = sizeof(T) == 4 ? 1 : 2;          // double2 boxes are described in 8-byte elements
         if (warp == 0) {
             // ---- loader: tickets, dependencies, box loads
+            // Tickets are taken two tiles ahead.  A block has ONE buffer in transit at a time (the other two are being
+            // transformed), and a first-pass box comes from DRAM: ~2 us from issue to arrival, during which the SM has
+            // 64 KiB in flight -- measured, that (bytes in flight / latency), not the butterflies, bounds the launch: ONE
+            // butterfly group per block delivers 87 - 105 % of what two do.  So the box of a first-pass ticket is prefetched
+            // into L2 the moment the ticket is taken, and the load that fills the buffer two tiles later is an L2 hit.
+            // (A ticket held here is never awaited by a tile with a smaller ticket, so holding two cannot deadlock.)
+            auto prefetch_tile = [&](const unsigned tk) {
+                if (!a.prefetch || tk >= total) return;
+                bool pa;
+                unsigned prow, pr;
+                decode_ticket(s, tk, pa, prow, pr);
+                if (!pa) return;
+                constexpr int ROWS = 1 << LG_N1;
+#pragma unroll
+                for (int r0 = 0; r0 < ROWS; r0 += BOX_A) {
+                    if constexpr (REAL == 2) {
+                        tma::prefetch_3d(&map_x, (int)pr * LH_A * ES, r0, (int)prow);
+                        tma::prefetch_3d(&map_x, ((1 << LG_N2) - (int)pr * LH_A - LH_A + 1) * ES, r0, (int)prow);
+                    } else {
+                        tma::prefetch_3d(&map_x, (int)pr * L_A * ES, r0, (int)prow);
+                    }
+                }
+            };
             unsigned pending = atomicAdd(s.ticket, 1u);
+            prefetch_tile(pending);
+            unsigned pending2 = atomicAdd(s.ticket, 1u);
+            prefetch_tile(pending2);
             unsigned t = 0;
             int exits_posted = 0;
             for (;; ++t) {
@@ -653,7 +687,9 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 unsigned row = 0, r = 0;
                 bool role_a = false;
                 if (!exit) {
-                    pending = atomicAdd(s.ticket, 1u);
+                    pending = pending2;
+                    pending2 = atomicAdd(s.ticket, 1u);
+                    prefetch_tile(pending2);
                     decode_ticket(s, ticket, role_a, row, r);
                     // the dependency: every first-pass tile of the row / the second pass of the row that used the
                     // work row before.  The block's own earlier tiles are published by the storer, which never
