@@ -266,6 +266,26 @@ inline size_t in_elem_size(const FftArgs &a, size_t real_size) {
     return (a.in_kind == IN_REAL || a.in_kind == IN_PAIRS) ? real_size : 2 * real_size;
 }
 
+// The packed-real bin-pair step fused into a TMA-fed launch (fft_tma.cuh, REAL): forward transforms leave as the bins
+// X[0..n] of the real transform (dst rows of pitch >= n + 1) or, with a spectrum, as the packed input z' of the inverse
+// transform of the fused filter.
+struct RealFuse {
+    const void *filt;          // forward: spectrum B[0..n], nullptr = rfft.  Inverse launches (irfft) read rows of n + 1 bins.
+};
+inline bool real_fuse_disabled() {
+    static const bool off = [] { const char *e = getenv("DSC_NO_REAL_FUSE"); return e != nullptr && *e != '\0' && *e != '0'; }();
+    return off;
+}
+// float32 filter: the fused forward launch is parity-green but measures 3 - 5 % SLOWER than transform + bin-pair sweep on
+// B200 (1.91 - 1.99 ms against 1.83 - 1.87 ms per GiB at 2^16 .. 2^20 samples): complex64 runs start 8 bytes off the 16-byte
+// granule of a bulk tensor store, so half of every tile leaves through the group's own stores, and the pair step (two
+// un-mix/mix steps, two spectrum bins per pair) doubles the instructions of a second-pass tile in a launch that is paced by
+// its instruction stream.  float64 gains 33 % (rfft) / 65 % (irfft).  Opt-in for float32: DSC_REAL_FUSE_F32=1 (tests do).
+inline bool real_fuse_f32() {
+    static const bool on = [] { const char *e = getenv("DSC_REAL_FUSE_F32"); return e != nullptr && *e == '1'; }();
+    return on;
+}
+
 
 #if !defined(DSC_EMUL)
 // ---- TMA-fed four-step (fft_tma.cuh): tensor maps and the launch -------------------------------------------------
@@ -306,26 +326,6 @@ bool encode_3d(CUtensorMap *map, const void *base, size_t elem_bytes, unsigned l
 inline bool tma_disabled() {
     static const bool off = [] { const char *e = getenv("DSC_NO_TMA"); return e != nullptr && *e != '\0' && *e != '0'; }();
     return off;
-}
-
-// The packed-real bin-pair step fused into a TMA-fed launch (fft_tma.cuh, REAL): forward transforms leave as the bins
-// X[0..n] of the real transform (dst rows of pitch >= n + 1) or, with a spectrum, as the packed input z' of the inverse
-// transform of the fused filter.
-struct RealFuse {
-    const void *filt;          // forward: spectrum B[0..n], nullptr = rfft.  Inverse launches (irfft) read rows of n + 1 bins.
-};
-inline bool real_fuse_disabled() {
-    static const bool off = [] { const char *e = getenv("DSC_NO_REAL_FUSE"); return e != nullptr && *e != '\0' && *e != '0'; }();
-    return off;
-}
-// float32 filter: the fused forward launch is parity-green but measures 3 - 5 % SLOWER than transform + bin-pair sweep on
-// B200 (1.91 - 1.99 ms against 1.83 - 1.87 ms per GiB at 2^16 .. 2^20 samples): complex64 runs start 8 bytes off the 16-byte
-// granule of a bulk tensor store, so half of every tile leaves through the group's own stores, and the pair step (two
-// un-mix/mix steps, two spectrum bins per pair) doubles the instructions of a second-pass tile in a launch that is paced by
-// its instruction stream.  float64 gains 33 % (rfft) / 65 % (irfft).  Opt-in for float32: DSC_REAL_FUSE_F32=1 (tests do).
-inline bool real_fuse_f32() {
-    static const bool on = [] { const char *e = getenv("DSC_REAL_FUSE_F32"); return e != nullptr && *e == '1'; }();
-    return on;
 }
 
 // Returns 1 when the shape is not covered (the caller continues with four_step_fused), 0 on success, < 0 on error.
