@@ -101,6 +101,9 @@ struct FusedEntry {
     int lg_n1, lg_n2, threads, lpb_a, lpb_b, smem;
     int grid;            // persistent launch: resident blocks on the whole device (set when first configured)
     bool configured;
+    // float factors <= 512: 16 points per thread (half the registers: four 256-thread blocks per SM)
+    void (*fn16)(const FftArgs, const FftArgs, const FourStepSync);
+    int lpb_a16, lpb_b16, smem16, grid16;
 };
 
 // block size of the fused launch: 64 payload registers per thread, 512 threads per SM.  Two 256-thread blocks
@@ -121,6 +124,12 @@ FusedEntry make_fused() {
     e.smem = fused_smem_bytes<T, LG_N1, LG_N2, THREADS>();
     e.grid = 0;
     e.configured = false;
+    e.fn16 = nullptr; e.lpb_a16 = e.lpb_b16 = e.smem16 = e.grid16 = 0;
+    if constexpr (sizeof(T) == 4 && LG_N1 <= 9 && LG_N2 <= 9 && THREADS == 256) {
+        e.fn16 = four_step_fused<T, LG_N1, LG_N2, THREADS, FWD, 4>;
+        e.lpb_a16 = THREADS >> (LG_N1 - 4); e.lpb_b16 = THREADS >> (LG_N2 - 4);
+        e.smem16 = fused_smem_bytes<T, LG_N1, LG_N2, THREADS, 4>();
+    }
     return e;
 }
 
@@ -155,6 +164,8 @@ struct TmaEntry {
     // the packed-real bin-pair step fused in: forward launches un-mix in the second pass (runs of at least 64 bytes);
     // inverse launches (double: float bin rows have an odd pitch no tensor map takes) mix in the first pass
     void (*fn_real)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
+    // finished tiles stored from the registers, buffers released after the last exchange (four_step_tma DIRECT)
+    void (*fn_direct)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaArgs, const FourStepSync);
     int lg_n1, lg_n2, l_a, l_b, box_a, box_b, smem;
     int grid;
     bool configured;
@@ -174,6 +185,7 @@ TmaEntry make_tma() {
         e.fn_real = four_step_tma<T, LG_N1, LG_N2, FWD, tma_lg_e<T>(), TMA_TILE_BYTES, 1>;
     if constexpr (!FWD && sizeof(T) == 8 && (tma_lines<T>(LG_N1) / 2) * (int)sizeof(cx<T>) >= 64 && (1 << LG_N1) / 2 <= TMA_GROUP_THREADS)
         e.fn_real = four_step_tma<T, LG_N1, LG_N2, FWD, tma_lg_e<T>(), TMA_TILE_BYTES, 2>;
+    e.fn_direct = four_step_tma<T, LG_N1, LG_N2, FWD, tma_lg_e<T>(), TMA_TILE_BYTES, 0, true>;
     e.lg_n1 = LG_N1; e.lg_n2 = LG_N2;
     e.l_a = tma_lines<T>(LG_N1); e.l_b = tma_lines<T>(LG_N2);
     e.box_a = tma_box_rows(LG_N1); e.box_b = tma_box_rows(LG_N2);

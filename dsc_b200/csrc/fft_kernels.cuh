@@ -893,15 +893,20 @@ DSC_DEV void spin_until(const unsigned *counter, const unsigned target) {
 }
 
 // shared-memory layout of the fused launch (elements): [ line buffers, max over the passes | 2 twiddle tables ]
-template <typename T, int LG_N1, int LG_N2, int THREADS> __host__ __device__ constexpr int fused_table_at() {
-    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+// LGE > 0 overrides the points per thread (log2) of both passes (the 16-point float variant: half the registers, twice the
+// resident warps)
+template <typename T> __host__ __device__ constexpr int fused_lg_e(int lge, int lg_n, int lg_other) {
+    return lge > 0 ? (lg_n < lge ? lg_n : lge) : pass_lg_e<T>(lg_n, lg_other);
+}
+template <typename T, int LG_N1, int LG_N2, int THREADS, int LGE = 0> __host__ __device__ constexpr int fused_table_at() {
+    constexpr int LG_E1 = fused_lg_e<T>(LGE, LG_N1, LG_N2), LG_E2 = fused_lg_e<T>(LGE, LG_N2, LG_N1);
     constexpr int A = PassTile<T, LG_N1, LG_E1, (THREADS >> (LG_N1 - LG_E1))>::LINES;
     constexpr int B = PassTile<T, LG_N2, LG_E2, (THREADS >> (LG_N2 - LG_E2))>::LINES;
     return A > B ? A : B;
 }
-template <typename T, int LG_N1, int LG_N2, int THREADS> __host__ __device__ constexpr int fused_smem_bytes() {
-    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2);
-    return (fused_table_at<T, LG_N1, LG_N2, THREADS>() +
+template <typename T, int LG_N1, int LG_N2, int THREADS, int LGE = 0> __host__ __device__ constexpr int fused_smem_bytes() {
+    constexpr int LG_E1 = fused_lg_e<T>(LGE, LG_N1, LG_N2);
+    return (fused_table_at<T, LG_N1, LG_N2, THREADS, LGE>() +
             2 * PassTile<T, LG_N1, LG_E1, (THREADS >> (LG_N1 - LG_E1))>::TABLE) * (int)sizeof(cx<T>);
 }
 
@@ -982,13 +987,13 @@ DSC_DEV void run_tickets(const FourStepSync &s, First &&first, Second &&second) 
     if (threadIdx.x == 0 && prev_done != nullptr) dsc_signal_release(prev_done);
 }
 
-template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD, int LGE = 0>
+__global__ void __launch_bounds__(THREADS, (LGE > 0 && LGE < (sizeof(T) == 4 ? 5 : 4) ? 1024 : 512) / THREADS)
 four_step_fused(const FftArgs a, const FftArgs b, const FourStepSync s) {
-    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+    constexpr int LG_E1 = fused_lg_e<T>(LGE, LG_N1, LG_N2), LG_E2 = fused_lg_e<T>(LGE, LG_N2, LG_N1);
     constexpr int LPB_A = THREADS >> (LG_N1 - LG_E1), LPB_B = THREADS >> (LG_N2 - LG_E2);
     static_assert(LPB_A >= 1 && LPB_B >= 1, "block too small for one line");
-    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS>();
+    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS, LGE>();
     DSC_DYN_SMEM(smem_raw);
     run_tickets(s,
         [&](unsigned row, unsigned r, int par, auto &before_scatter) {

@@ -360,10 +360,12 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
         cudaError_t err = cudaFuncSetAttribute((const void *)te->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
         if (err == cudaSuccess && te->fn_real != nullptr)
             err = cudaFuncSetAttribute((const void *)te->fn_real, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
+        if (err == cudaSuccess && te->fn_direct != nullptr)
+            err = cudaFuncSetAttribute((const void *)te->fn_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem);
         if (err == cudaSuccess && te->fn16 != nullptr) {
             err = cudaFuncSetAttribute((const void *)te->fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, te->smem16);
             int per_sm = 0;
-            if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)te->fn16, TMA_THREADS, te->smem16);
+            if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)te->fn16, TMA4_THREADS, te->smem16);
             te->ctas16 = per_sm;
         }
         int dev = 0, sms = 0;
@@ -395,6 +397,8 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
         // a tile is published about five tile times after its ticket was taken (two of them waiting in the loader), while the whole GPU takes
         // ~grid tickets per tile time: put a row's second pass that far behind its first pass
         long long lag = (5LL * resident + tiles_b + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
+        static const long long lag_env = [] { const char *e = getenv("DSC_TMA_LAG"); return e ? atoll(e) : 0LL; }();
+        if (lag_env > 0) lag = lag_env;
         if (lag < 1) lag = 1;
         if (ring > 0 && lag > ring / 2) lag = ring / 2;
         if (lag > rows) lag = rows;
@@ -427,20 +431,25 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
     a.discard_work = !no_discard;
     static const bool no_prefetch = [] { const char *e = getenv("DSC_TMA_PREFETCH"); return e != nullptr && *e == '0'; }();
     a.prefetch = !no_prefetch;
+    a.out = dst; a.out_pitch = dst_row_stride;
     if (rf != nullptr) {
         a.twr_lo = p->tw_real_lo; a.twr_hi = p->tw_real_hi;
         a.real_shift = p->real_shift; a.real_mask = (1 << p->real_shift) - 1;
         a.filt = rf->filt;
-        a.out = dst; a.out_pitch = dst_row_stride;
         a.in = first.x; a.in_pitch = first.gi.ostride;
     }
+    static const int debug_skip = [] { const char *e = getenv("DSC_TMA_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+    a.debug_skip = debug_skip;
+    static const bool want_direct = [] { const char *e = getenv("DSC_TMA_DIRECT"); return e != nullptr && *e == '1'; }();
+    const bool direct = want_direct && rf == nullptr && !e16 && te->fn_direct != nullptr;
     const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
     if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
     const long long tiles = rows * (tiles_a + tiles_b);
     const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
-    if (rf != nullptr) te->fn_real<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
-    else if (e16) te->fn16<<<blocks, TMA_THREADS, te->smem16, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
-    else te->fn<<<blocks, TMA_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    if (rf != nullptr) te->fn_real<<<blocks, TMA4_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    else if (direct) te->fn_direct<<<blocks, TMA4_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    else if (e16) te->fn16<<<blocks, TMA4_THREADS, te->smem16, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
+    else te->fn<<<blocks, TMA4_THREADS, te->smem, (cudaStream_t)stream>>>(map_x, map_w, map_out, a, s);
     return check_launch("four_step_tma");
 }
 // Which line lengths (log2) go to the cluster kernels.  Measured on B200 (profiles/r2_two_pass_lengths.md): they read and
@@ -645,6 +654,59 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
 
     FusedEntry *fe = fused_entry<T, FWD>(p->lg_n1, p->lg_n2);
     const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
+#if !defined(DSC_EMUL)
+    // 16 points per thread (register-direct, four blocks per SM): dense complex rows only
+    static const bool want_f16 = [] { const char *e = getenv("DSC_FUSED_E16"); return e != nullptr && *e == '1'; }();
+    if (want_f16 && fe != nullptr && fe->fn16 != nullptr && p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr &&
+        first.in_kind == IN_COMPLEX && first.in_limit >= n && first.seg_shift == 0 &&
+        rows * (n2 / fe->lpb_a16 + n1 / fe->lpb_b16) < 0x7fffffffLL && work != nullptr && work_bytes >= sync_bytes + row_bytes) {
+        set_stage_tables<T>(a, p->tw1_e16);
+        set_stage_tables<T>(b, p->tw2_e16);
+        const size_t l2_budget = 64u << 20;
+        long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
+        const long long cap = (long long)(l2_budget / row_bytes) > 4 ? (long long)(l2_budget / row_bytes) : 4;
+        if (ring > cap) ring = cap;
+        if (ring >= rows) ring = 0;
+        if (fe->grid16 == 0) {
+            if (fe->smem16 > 48 * 1024) {
+                const cudaError_t err = cudaFuncSetAttribute((const void *)fe->fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, fe->smem16);
+                if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
+            }
+            int per_sm = 0, dev = 0, sms = 0;
+            cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fe->fn16, fe->threads, fe->smem16);
+            if (err == cudaSuccess) err = cudaGetDevice(&dev);
+            if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (err != cudaSuccess || per_sm < 1) return fail(DSC_CUDA_ELAUNCH, "occupancy query: %s", cudaGetErrorString(err));
+            fe->grid16 = per_sm * sms;
+            if (getenv("DSC_DEBUG_OCC")) fprintf(stderr, "four_step_fused e16: %d blocks per SM, smem %d\n", per_sm, fe->smem16);
+        }
+        FourStepSync s{};
+        s.ticket = (unsigned *)work;
+        s.a_done = s.ticket + 1;
+        s.b_done = s.a_done + rows;
+        s.tiles_a = (int)(n2 / fe->lpb_a16);
+        s.tiles_b = (int)(n1 / fe->lpb_b16);
+        s.ring = (int)ring;
+        s.rows = (int)rows;
+        {
+            long long lag = (3LL * fe->grid16 + s.tiles_a + s.tiles_b - 1) / (s.tiles_a + s.tiles_b);
+            if (lag < 1) lag = 1;
+            if (ring > 0 && lag > ring / 2) lag = ring / 2;
+            if (lag > rows) lag = rows;
+            s.lag = (int)lag;
+        }
+        V *mid = (V *)((char *)work + sync_bytes);
+        a.out = mid; a.lines = rows * n2; a.ring_out = ring; a.inner_shift = p->lg_n2;
+        a.no_limit = 1;
+        b.x = mid; b.out = dst; b.lines = rows * n1; b.ring_in = ring; b.inner_shift = p->lg_n1;
+        const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
+        if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
+        const long long tiles = rows * (s.tiles_a + s.tiles_b);
+        const unsigned blocks = (unsigned)(tiles < fe->grid16 ? tiles : fe->grid16);
+        DSC_LAUNCH(fe->fn16, blocks, fe->threads, fe->smem16, stream, a, b, s);
+        return check_launch("four_step_fused e16");
+    }
+#endif
     if (fe != nullptr && rows * (n2 / fe->lpb_a + n1 / fe->lpb_b) < 0x7fffffffLL &&
         work != nullptr && work_bytes >= sync_bytes + row_bytes) {
         // ring of work rows: as many as fit, but no more than keeps the intermediate inside L2

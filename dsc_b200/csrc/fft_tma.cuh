@@ -120,6 +120,13 @@ DSC_DEV void store_linear(void *gdst, const void *src, unsigned bytes, unsigned 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                  ::"l"(gdst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
 }
+// register -> global with an L2 eviction hint (the direct-store tiles: work rows evict_last, results evict_first)
+DSC_DEV void st_hint(float2 *p, const float2 v, const unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+DSC_DEV void st_hint(double2 *p, const double2 v, const unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 DSC_DEV void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DSC_DEV void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DSC_DEV void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -135,7 +142,13 @@ constexpr int TMA_BUFFERS = 3;
 #endif
 constexpr int TMA_GROUPS = DSC_TMA_GROUPS;                 // consumer groups of TMA_GROUP_THREADS threads
 constexpr int TMA_GROUP_THREADS = 256;
-constexpr int TMA_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 64;     // + the loader warp and the storer warp
+constexpr int TMA_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 64;     // + the loader warp and the storer warp (fft_cluster_pipe)
+// four_step_tma: the loader warp and one storer warp PER BUFFER.  A storer's chain per tile -- bulk store, wait until it has
+// read the buffer, wait until it has completed, proxy fence, release of the row counter -- is ~5000 cycles of pure latency;
+// with a single storer that chain, not the memory system and not the butterflies, was the launch's period (a launch whose
+// groups pass the tiles through untouched ran no faster than the full transform: tools/micro/two_pass_copy.cu).
+constexpr int TMA4_THREADS = TMA_GROUPS * TMA_GROUP_THREADS + 32 * (1 + TMA_BUFFERS);
+constexpr int TMA_DONE_RING = 8;                           // a group is never more than three tiles ahead of the storer
 
 template <typename T> __host__ __device__ constexpr int tma_lg_e() { return sizeof(T) == 4 ? 5 : 4; }     // 32 / 16 points per thread
 template <typename T> __host__ __device__ constexpr int tma_tile_points() { return TMA_TILE_BYTES / (int)sizeof(cx<T>); }
@@ -164,6 +177,8 @@ struct TmaArgs {
     const void *in;                // REAL == 2: the bin rows X[0..n] (for the one column no box load covers)
     long long in_pitch;
     int prefetch;                  // first-pass boxes are prefetched into L2 when their ticket is taken, two tiles ahead
+    int debug_skip;                // timing experiments only (wrong results): 1 = tiles pass through untouched, 2 = only the
+                                   // shared-memory traffic of a tile (two round trips per point), no arithmetic
 };
 
 struct TmaTileDesc { unsigned role_a, row, r, exit; };
@@ -181,6 +196,9 @@ template <typename T, int TILE = TMA_TILE_BYTES> struct TmaSmem {
     unsigned long long posted[TMA_BUFFERS];        // desc[b] names the tile that is on its way (loader -> groups)
     TmaTileDesc desc[TMA_BUFFERS];
     V ladder[2][5 * 32];                           // the stage-1 twiddle rows of the two passes (TmaTile::ladder_fill)
+    // direct-store launches: tile t's stores have been issued by every warp of its group (groups -> storer), ring over t
+    unsigned long long done[TMA_DONE_RING];
+    TmaTileDesc sdesc[TMA_DONE_RING];
 };
 
 // W_n^p from the two sqrt(n)-sized tables
@@ -258,9 +276,18 @@ struct TmaTile {
             }
         }
     }
+    // rel: optional mbarrier a warp arrives on once its threads have read their last-stage inputs, the last time the tile
+    // touches its buffer (direct-store tiles: the loader may refill the buffer while the last stage and the stores run)
+    static DSC_DEV void release_buffer(const unsigned rel) {      // shared-window address of the mbarrier, 0 = none
+        if (rel != 0u) {
+            tma::fence_async_smem();           // this thread's exchange writes before the bulk copy that overwrites them
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rel) : "memory");
+        }
+    }
     template <int S>
     static DSC_DEV void stage(V (&v)[E], V *buf, const int l, const int j, const int l_last, const int j_last,
-                              const void *const *tw_all, const int bar_id, const V *lad = nullptr) {
+                              const void *const *tw_all, const int bar_id, const V *lad = nullptr, const unsigned rel = 0u) {
         constexpr int LG_R = Sc::lg_r(S), R = 1 << LG_R, NB = E / R;
         constexpr int LG_NS = S * LG_E, NS = 1 << LG_NS;
         constexpr bool LAST = S == STAGES - 1;
@@ -311,7 +338,8 @@ struct TmaTile {
             const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
 #pragma unroll
             for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
-            stage<S + 1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id, lad);
+            if constexpr (S + 1 == STAGES - 1) release_buffer(rel);
+            stage<S + 1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id, lad, rel);
         }
     }
 
@@ -344,9 +372,15 @@ struct TmaTile {
         return tma_twiddle<T>(a, line_q(u, (unsigned)l_last, n_other) * (unsigned)j_last);
     }
 
+    // gout != nullptr (direct-store tiles): the finished points leave from the registers -- gout is this thread's first
+    // output element, its other points follow at a compile-time pitch (TRANSPOSE: TT elements, the thread's line of the work
+    // row; else TT << LG_OS, the result's rows of 2^LG_OS bins) -- and the buffer is released through `rel` right after the
+    // last exchange instead of carrying the finished tile to a bulk store.
+    template <int LG_OS = 0>
     static DSC_DEV void run(V *buf, V *table, const TmaArgs &a, const void *const *tw_all, const unsigned q0,
                             const int gtid, const int bar_id, const V *lad = nullptr, const bool prepared = false,
-                            V w0 = V{}) {
+                            V w0 = V{}, void *const obase = nullptr, const unsigned line0 = 0u, const int keep = 0,
+                            const unsigned rel = 0u) {
         const int l = gtid % L, j = gtid / L;
         const int l_last = TRANSPOSE ? gtid / TT : l, j_last = TRANSPOSE ? gtid % TT : j;
         V v[E];
@@ -355,7 +389,30 @@ struct TmaTile {
         if constexpr (TRANSPOSE) {
             if (!prepared) w0 = tma_twiddle<T>(a, (q0 + (unsigned)l_last) * (unsigned)j_last);
         }
-        stage_first(v, buf, table, a, l, j, l_last, j_last, tw_all, q0, gtid, bar_id, lad, prepared);
+        stage_first(v, buf, table, a, l, j, l_last, j_last, tw_all, q0, gtid, bar_id, lad, prepared, rel);
+        if (obase != nullptr) {
+            // address and policy are built here, after the butterflies: nothing 64-bit lives through the transform
+            if constexpr (TRANSPOSE) {
+                const unsigned long long pol = tma::policy_evict_last();
+                V *gout = (V *)obase + (((long long)line0 + l_last) << LG_N) + j_last;
+#pragma unroll
+                for (int c = 0; c < E; ++c) {
+                    const V w = c == 0 ? w0 : cmul(w0, table[c * L + l_last]);
+                    tma::st_hint(gout + c * TT, cmul_tw<FWD>(v[c], w), pol);
+                }
+            } else {
+                const unsigned long long pol = keep ? tma::policy_evict_last() : tma::policy_evict_first();
+                V *gout = (V *)obase + line0 + l + ((long long)j << LG_OS);
+                if (a.do_scale) {
+                    const T s = (T)a.scale;
+#pragma unroll
+                    for (int c = 0; c < E; ++c) { v[c].x *= s; v[c].y *= s; }
+                }
+#pragma unroll
+                for (int c = 0; c < E; ++c) tma::st_hint(gout + ((long long)(c * TT) << LG_OS), v[c], pol);
+            }
+            return;
+        }
         // every thread has read its last-stage inputs: the buffer may take the finished tile
         dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
         if constexpr (TRANSPOSE) {
@@ -380,7 +437,8 @@ struct TmaTile {
     // stage 0 with the table build folded in after its first barrier
     static DSC_DEV void stage_first(V (&v)[E], V *buf, V *table, const TmaArgs &a, const int l, const int j,
                                     const int l_last, const int j_last, const void *const *tw_all, const unsigned q0,
-                                    const int gtid, const int bar_id, const V *lad = nullptr, const bool prepared = false) {
+                                    const int gtid, const int bar_id, const V *lad = nullptr, const bool prepared = false,
+                                    const unsigned rel = 0u) {
         static_assert(STAGES >= 2, "a pass has at least one exchange");
         constexpr int R = 1 << Sc::lg_r(0), NB = E / R;
         static_assert(NB == 1, "the first stage is a full-radix butterfly");
@@ -402,7 +460,8 @@ struct TmaTile {
         const int ln = NEXT_JFAST ? l_last : l, jn = NEXT_JFAST ? j_last : j;
 #pragma unroll
         for (int c = 0; c < E; ++c) v[c] = buf[phys<NEXT_JFAST>(jn + c * TT, ln)];
-        stage<1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id, lad);
+        if constexpr (1 == STAGES - 1) release_buffer(rel);
+        stage<1>(v, buf, ln, jn, l_last, j_last, tw_all, bar_id, lad, rel);
     }
 };
 
@@ -607,8 +666,13 @@ DSC_DEV void tma_mix_tile(cx<T> *buf, const TmaArgs &a, const unsigned u, const 
 // passes of up to 512 points (32-byte rows beyond that).
 // REAL: 0 = complex rows; 1 = forward with the packed-real bin-pair step fused into the second pass (tma_unmix_tile);
 // 2 = inverse whose first pass builds the packed points from the bins of the real transform (tma_mix_tile).
-template <typename T, int LG_N1, int LG_N2, bool FWD, int LGE = tma_lg_e<T>(), int TILE = TMA_TILE_BYTES, int REAL = 0>
-__global__ void __launch_bounds__(TMA_THREADS, (TILE * 2 <= TMA_TILE_BYTES ? 2 : 1))
+// DIRECT: finished tiles leave from the registers (coalesced st.global, runs of 64 - 256 bytes) instead of going back into
+// the buffer for a bulk store, and a tile gives its buffer back right after its last exchange.  A buffer is then held for
+// load + half a transform instead of load + transform + store, so with the same three buffers more loads are in flight --
+// bytes in flight per SM, not the butterflies, bound the bulk-store variant (one group delivers 87 - 105 % of two).  The
+// storer thread only publishes row counters (after every warp of the group has issued its stores).
+template <typename T, int LG_N1, int LG_N2, bool FWD, int LGE = tma_lg_e<T>(), int TILE = TMA_TILE_BYTES, int REAL = 0, bool DIRECT = false>
+__global__ void __launch_bounds__(TMA4_THREADS, (TILE * 2 <= TMA_TILE_BYTES ? 2 : 1))
 four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const __grid_constant__ CUtensorMap map_out, const TmaArgs a, const FourStepSync s) {
     using V = cx<T>;
@@ -624,6 +688,8 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                   "fused packed-real tiles: runs of at least 64 bytes, one pair of the middle column per thread");
     using Smem = TmaSmem<T, TILE>;
     static_assert(L_A * TileA::E <= Smem::TABLE_MAX, "inter-pass table");
+    static_assert(!DIRECT || REAL == 0, "direct stores: complex rows only");
+    constexpr int GROUP_WARPS = TMA_GROUP_THREADS / 32;
     DSC_DYN_SMEM(smem_raw);
     // the tile buffers want 1024-byte alignment (box destinations): round the dynamic window up
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -632,15 +698,16 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (tid == 0) {
         for (int b = 0; b < TMA_BUFFERS; ++b) {
             tma::mbar_init(&sm.full[b], 1);
-            tma::mbar_init(&sm.ready[b], TMA_GROUP_THREADS);
-            tma::mbar_init(&sm.empty[b], 1);
+            tma::mbar_init(&sm.ready[b], GROUP_WARPS);     // one arrival per warp of the group
+            tma::mbar_init(&sm.empty[b], DIRECT ? GROUP_WARPS : 1);
             tma::mbar_init(&sm.posted[b], 1);
         }
+        for (int i = 0; i < TMA_DONE_RING; ++i) tma::mbar_init(&sm.done[i], GROUP_WARPS);
         tma::fence_barrier_init();
     }
     static_assert(TileA::LADDER_ELEMS <= 5 * 32 && TileB::LADDER_ELEMS <= 5 * 32, "ladder rows");
-    TileA::ladder_fill(sm.ladder[0], a.tw_a, tid, TMA_THREADS);
-    TileB::ladder_fill(sm.ladder[1], a.tw_b, tid, TMA_THREADS);
+    TileA::ladder_fill(sm.ladder[0], a.tw_a, tid, TMA4_THREADS);
+    TileB::ladder_fill(sm.ladder[1], a.tw_b, tid, TMA4_THREADS);
     __syncthreads();
 
     const unsigned total = (unsigned)s.rows * (unsigned)(s.tiles_a + s.tiles_b);
@@ -715,11 +782,16 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 const int b = (int)(t % TMA_BUFFERS);
                 if (t >= TMA_BUFFERS) tma::mbar_wait(&sm.empty[b], (t / TMA_BUFFERS - 1) & 1, "loader: empty");
                 if (exit) {
-                    // no more tiles: one more turn for each group (and the storer), then leave
+                    // no more tiles: one more turn for each group and each storer, then leave.  The first TMA_GROUPS exit
+                    // tiles are passed on to the storers by the groups; for the others the groups are gone and this thread
+                    // arrives in their place.
+                    constexpr int EXITS = DIRECT ? TMA_GROUPS : (TMA_GROUPS > TMA_BUFFERS ? TMA_GROUPS : TMA_BUFFERS);
                     sm.desc[b] = TmaTileDesc{0u, 0u, 0u, 1u};
                     tma::mbar_arrive(&sm.posted[b]);
                     tma::mbar_arrive(&sm.full[b]);
-                    if (++exits_posted == TMA_GROUPS) break;
+                    if (exits_posted >= TMA_GROUPS)
+                        for (int i = 0; i < GROUP_WARPS; ++i) tma::mbar_arrive(&sm.ready[b]);
+                    if (++exits_posted == EXITS) break;
                     continue;
                 }
                 sm.desc[b] = TmaTileDesc{role_a ? 1u : 0u, row, r, 0u};
@@ -755,34 +827,29 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     }
                 }
             }
-        } else {
-            // ---- storer: finished tiles leave; their rows' counters are published once the copies have completed
-            TmaTileDesc unpublished[2];
-            int n_unpublished = 0;
-            auto publish = [&](const int keep) {        // all but the `keep` most recent stores
-                if (n_unpublished <= keep) return;
-                if (keep == 0) tma::store_wait_all(); else tma::store_wait_all_but_one();
-                tma::fence_async_all();                 // async-proxy writes before the generic-proxy release below
-                for (int i = 0; i < n_unpublished - keep; ++i) {
-                    const TmaTileDesc d = unpublished[i];
-                    dsc_signal_release((d.role_a ? s.a_done : s.b_done) + d.row);
-                }
-                if (keep) unpublished[0] = unpublished[n_unpublished - 1];
-                n_unpublished = keep < n_unpublished ? keep : n_unpublished;
-            };
+        } else if constexpr (DIRECT) {
+            if (warp != 1) return;
+            // ---- publisher: a tile's row counter once every warp of its group has issued the tile's stores.  The warps'
+            // stores happen before their arrivals, the arrivals before this wait: the release below covers them.
             int exits = 0;
             for (unsigned st = 0;; ++st) {
-                const int b = (int)(st % TMA_BUFFERS);
-                const unsigned par = (st / TMA_BUFFERS) & 1;
-                if (!tma::mbar_test_wait(&sm.ready[b], par)) {
-                    publish(0);                         // nothing to do anyway: other blocks may be waiting for these
-                    tma::mbar_wait(&sm.ready[b], par, "storer: ready");
-                }
-                const TmaTileDesc d = sm.desc[b];
+                const int i = (int)(st % TMA_DONE_RING);
+                tma::mbar_wait(&sm.done[i], (st / TMA_DONE_RING) & 1, "publisher: done");
+                const TmaTileDesc d = sm.sdesc[i];
                 if (d.exit) {
                     if (++exits == TMA_GROUPS) break;
                     continue;
                 }
+                dsc_signal_release((d.role_a ? s.a_done : s.b_done) + d.row);
+            }
+        } else {
+            // ---- storer of buffer warp - 1: its finished tiles leave; a tile's row counter is published once the copy has
+            // completed.  Nothing here waits for another storer, the loader or a group's later tile.
+            const int b = warp - 1;
+            for (unsigned st = (unsigned)b;; st += TMA_BUFFERS) {
+                tma::mbar_wait(&sm.ready[b], (st / TMA_BUFFERS) & 1, "storer: ready");
+                const TmaTileDesc d = sm.desc[b];
+                if (d.exit) break;
                 if (d.role_a) {
                     // L_A contiguous lines W[q0 + l][k1] of the work row
                     const long long wrow = a.ring ? d.row % a.ring : d.row;
@@ -798,8 +865,8 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                             tma::store_linear(wr + ((long long)(1 << LG_N2) / 2 << LG_N1), sm.buf[b] + (2 * LH_A - 1) * LINE, LINE, pol_keep);
                         }
                     } else {
-                    V *dst = (V *)a.work + ((wrow << LG_N2) + (long long)d.r * L_A << LG_N1);
-                    tma::store_linear(dst, sm.buf[b], TMA_TILE_BYTES, pol_keep);
+                        V *dst = (V *)a.work + ((wrow << LG_N2) + (long long)d.r * L_A << LG_N1);
+                        tma::store_linear(dst, sm.buf[b], TMA_TILE_BYTES, pol_keep);
                     }
                 } else {
                     constexpr int ROWS = 1 << LG_N2;
@@ -821,10 +888,10 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 tma::store_commit();
                 tma::store_wait_read();
                 tma::mbar_arrive(&sm.empty[b]);         // the loader may refill the buffer (and overwrite desc[b])
-                unpublished[n_unpublished++] = d;
-                publish(1);
+                tma::store_wait_all();
+                tma::fence_async_all();                 // async-proxy writes before the generic-proxy release below
+                dsc_signal_release((d.role_a ? s.a_done : s.b_done) + d.row);
             }
-            publish(0);
         }
         return;
     }
@@ -849,13 +916,49 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 xm_b = __ldg(xr + ((long long)((1 << LG_N1) - 1 - gtid) << LG_N2));
             }
         }
+        if constexpr (DIRECT) {
+            if (gtid == 0) sm.sdesc[t % TMA_DONE_RING] = d;
+        }
         tma::mbar_wait(&sm.full[b], (t / TMA_BUFFERS) & 1, "group: full");
-        if (d.exit) { tma::mbar_arrive(&sm.ready[b]); break; }
+        if (d.exit) {
+            if constexpr (DIRECT) { if ((tid & 31) == 0) tma::mbar_arrive(&sm.done[t % TMA_DONE_RING]); }
+            else if ((tid & 31) == 0) tma::mbar_arrive(&sm.ready[b]);
+            break;
+        }
         V *buf = reinterpret_cast<V *>(sm.buf[b]);
         if constexpr (REAL == 2) {
             if (d.role_a) tma_mix_tile<T, LG_N1, LG_N2, L_A>(buf, a, d.r, gtid, bar_id, xm_a, xm_b);
         }
-        if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id, sm.ladder[0], true, w0);
+        if (!DIRECT && REAL == 0 && a.debug_skip != 0) {
+            if (a.debug_skip == 2) {
+                volatile V *vb = buf;
+                constexpr int PTS = TMA_TILE_BYTES / (int)sizeof(V) / TMA_GROUP_THREADS;
+                V v[PTS];
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+                    for (int c = 0; c < PTS; ++c) { v[c].x = vb[gtid + c * TMA_GROUP_THREADS].x; v[c].y = vb[gtid + c * TMA_GROUP_THREADS].y; }
+                    dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
+#pragma unroll
+                    for (int c = 0; c < PTS; ++c) { vb[gtid + c * TMA_GROUP_THREADS].x = v[c].x; vb[gtid + c * TMA_GROUP_THREADS].y = v[c].y; }
+                    dsc_group_barrier(bar_id, TMA_GROUP_THREADS);
+                }
+            }
+            tma::fence_async_smem();
+            __syncwarp();
+            if ((tid & 31) == 0) tma::mbar_arrive(&sm.ready[b]);
+            continue;
+        }
+        if constexpr (DIRECT) {
+            if (d.role_a) {
+                // this thread's run of the work line W[q0 + l_last][j_last + c TT]
+                const long long wrow = a.ring ? d.row % a.ring : d.row;
+                TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id, sm.ladder[0], true, w0,
+                           (V *)a.work + ((wrow << LG_N2) << LG_N1), d.r * (unsigned)L_A, 1, tma::smem_u32(&sm.empty[b]));
+            }
+        }
+        if (DIRECT && d.role_a) {}
+        else if (d.role_a) TileA::run(buf, sm.table[group], a, a.tw_a, d.r * (unsigned)L_A, gtid, bar_id, sm.ladder[0], true, w0);
         else {
             constexpr int RUNS = REAL == 1 ? 2 : 1, RUN_BYTES = (REAL == 1 ? LH_B : L_B) * (int)sizeof(V);
             if constexpr (RUN_BYTES >= 128) {
@@ -878,11 +981,24 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     }
                 }
             }
-            TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id, sm.ladder[1]);
+            if constexpr (DIRECT) {
+                // bins k1 + n1 (j + c TT) of the result row, k1 = r L_B + l
+                TileB::template run<LG_N1>(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id, sm.ladder[1], false, V{},
+                                           (V *)a.out + (long long)d.row * a.out_pitch, d.r * (unsigned)L_B, a.keep_out,
+                                           tma::smem_u32(&sm.empty[b]));
+            } else {
+                TileB::run(buf, sm.table[group], a, a.tw_b, 0u, gtid, bar_id, sm.ladder[1]);
+            }
             if constexpr (REAL == 1) tma_unmix_tile<T, LG_N1, LG_N2, L_B>(buf, a, d.r, d.row, gtid, bar_id);
         }
-        tma::fence_async_smem();
-        tma::mbar_arrive(&sm.ready[b]);
+        if constexpr (DIRECT) {
+            __syncwarp();
+            if ((tid & 31) == 0) tma::mbar_arrive(&sm.done[t % TMA_DONE_RING]);
+        } else {
+            tma::fence_async_smem();                    // this thread's writes of the finished tile before the bulk store
+            __syncwarp();
+            if ((tid & 31) == 0) tma::mbar_arrive(&sm.ready[b]);
+        }
     }
 }
 
