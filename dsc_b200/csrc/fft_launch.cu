@@ -343,9 +343,12 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
                           (FWD ? dst_row_stride < n + (rf->filt ? 0 : 1) : (first.in_limit < n + 1 || first.gi.ostride < n + 1))))
         return 1;
     // 16 points per thread on 32 KiB tiles, two blocks per SM (twice the butterfly warps), where the plan carries its tables.
-    // Measured on B200: 2914 / 2778 / 2580 / 2508 GB/s at 2^15 .. 2^18 against 3060 / 2994 / 2844 / 2739 for 32 points per
-    // thread -- doubling the warps does not help, so it is opt-in (DSC_TMA_E16=1; the GPU parity tests run it).
-    static const bool want_e16 = [] { const char *e = getenv("DSC_TMA_E16"); return e != nullptr && *e == '1'; }();
+    // With one storer warp per buffer the launch is no longer paced by its copy pipeline and the extra warps pay where the
+    // half-size tiles still have 128-byte rows: passes of at most 256 points (2^15: 3338 -> 3586 GB/s, 2^16: 3340 -> 3534).
+    // 512-point passes would have 64-byte rows (2^17 / 2^18: 2675 / 2564 against 3386 / 3349) and keep 32 points per thread.
+    // DSC_TMA_E16=0 / 1 forces it off / on wherever the tables exist (the GPU parity tests run both).
+    static const int e16_env = [] { const char *e = getenv("DSC_TMA_E16"); return e == nullptr || *e == '\0' ? -1 : atoi(e); }();
+    const bool want_e16 = e16_env < 0 ? (p->lg_n1 <= 8 && p->lg_n2 <= 8) : e16_env != 0;
     bool e16 = te->fn16 != nullptr && p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr && want_e16 && rf == nullptr;
     // dense complex rows, read in full, 16-byte aligned rows on both sides
     if (first.in_kind != IN_COMPLEX || first.in_limit < n || first.seg_shift != 0 || first.gi.lstride != 1 || first.gi.estride != n2 ||

@@ -719,18 +719,11 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         constexpr int ES = sizeof(T) == 4 ? 1 : 2;          // double2 boxes are described in 8-byte elements
         if (warp == 0) {
             // ---- loader: tickets, dependencies, box loads
-            // Tickets are taken two tiles ahead.  A block has ONE buffer in transit at a time (the other two are being
-            // transformed), and a first-pass box comes from DRAM: ~2 us from issue to arrival, during which the SM has
-            // 64 KiB in flight -- measured, that (bytes in flight / latency), not the butterflies, bounds the launch: ONE
-            // butterfly group per block delivers 87 - 105 % of what two do.  So the box of a first-pass ticket is prefetched
-            // into L2 the moment the ticket is taken, and the load that fills the buffer two tiles later is an L2 hit.
+            // Tickets are taken two tiles ahead, and (a.prefetch) the boxes of a first-pass tile are prefetched into L2 when
+            // the tile is looked up, one tile before the load that fills its buffer.
             // (A ticket held here is never awaited by a tile with a smaller ticket, so holding two cannot deadlock.)
-            auto prefetch_tile = [&](const unsigned tk) {
-                if (!a.prefetch || tk >= total) return;
-                bool pa;
-                unsigned prow, pr;
-                decode_ticket(s, tk, pa, prow, pr);
-                if (!pa) return;
+            auto prefetch_boxes = [&](const bool pa, const unsigned prow, const unsigned pr) {
+                if (!a.prefetch || !pa) return;
                 constexpr int ROWS = 1 << LG_N1;
 #pragma unroll
                 for (int r0 = 0; r0 < ROWS; r0 += BOX_A) {
@@ -742,42 +735,58 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     }
                 }
             };
+            // One tile ahead of the one being issued, its ticket is decoded and its row counter read once (the value is only
+            // looked at an iteration later): the two L2 round trips of a tile -- the ticket and the counter -- overlap with
+            // the waits of the tile before instead of adding to every tile's issue.
+            struct Pending {
+                unsigned ticket, row, r, target, seen;
+                bool exit, role_a;
+                const unsigned *flag;
+            };
+            auto lookup = [&](const unsigned ticket) {
+                Pending n{ticket, 0u, 0u, 0u, 0u, ticket >= total, false, nullptr};
+                if (!n.exit) {
+                    decode_ticket(s, ticket, n.role_a, n.row, n.r);
+                    // the dependency: every first-pass tile of the row / the second pass of the row that used the
+                    // work row before.  The block's own earlier tiles are published by the storers, which never
+                    // wait for this thread.
+                    if (!n.role_a) { n.flag = s.a_done + n.row; n.target = (unsigned)s.tiles_a; }
+                    else if (s.ring && n.row >= (unsigned)s.ring) { n.flag = s.b_done + (n.row - s.ring); n.target = (unsigned)s.tiles_b; }
+                    if (n.flag != nullptr) n.seen = ld_acquire(n.flag);
+                    prefetch_boxes(n.role_a, n.row, n.r);
+                }
+                return n;
+            };
             unsigned pending = atomicAdd(s.ticket, 1u);
-            prefetch_tile(pending);
             unsigned pending2 = atomicAdd(s.ticket, 1u);
-            prefetch_tile(pending2);
+            Pending cur = lookup(pending);
             unsigned t = 0;
             int exits_posted = 0;
             for (;; ++t) {
-                const unsigned ticket = pending;
-                const bool exit = ticket >= total;
-                unsigned row = 0, r = 0;
-                bool role_a = false;
+                const unsigned ticket = cur.ticket;
+                const bool exit = cur.exit;
+                const unsigned row = cur.row, r = cur.r;
+                const bool role_a = cur.role_a;
+                Pending nxt = cur;
                 if (!exit) {
-                    pending = pending2;
-                    pending2 = atomicAdd(s.ticket, 1u);
-                    prefetch_tile(pending2);
-                    decode_ticket(s, ticket, role_a, row, r);
-                    // the dependency: every first-pass tile of the row / the second pass of the row that used the
-                    // work row before.  The block's own earlier tiles are published by the storer, which never
-                    // waits for this thread.
-                    const unsigned *flag = nullptr;
-                    unsigned target = 0;
-                    if (!role_a) { flag = s.a_done + row; target = (unsigned)s.tiles_a; }
-                    else if (s.ring && row >= (unsigned)s.ring) { flag = s.b_done + (row - s.ring); target = (unsigned)s.tiles_b; }
-                    if (flag != nullptr) {
-                        const long long t0 = clock64();
-                        while (ld_acquire(flag) < target) {
-                            __nanosleep(64);
-                            if (clock64() - t0 > (1LL << 32)) {
-                                printf("dsc(cuda): block %u loader stuck on the row counter of %s row %u (have %u, need %u), ticket %u\n",
-                                       blockIdx.x, role_a ? "second-pass" : "first-pass", role_a ? row - s.ring : row, ld_acquire(flag), target, ticket);
-                                __trap();
+                    nxt = lookup(pending2);
+                    pending2 = atomicAdd(s.ticket, 1u);      // looked up an iteration from now
+                    if (cur.flag != nullptr) {
+                        if (cur.seen < cur.target) {
+                            const long long t0 = clock64();
+                            while (ld_acquire(cur.flag) < cur.target) {
+                                __nanosleep(64);
+                                if (clock64() - t0 > (1LL << 32)) {
+                                    printf("dsc(cuda): block %u loader stuck on the row counter of %s row %u (have %u, need %u), ticket %u\n",
+                                           blockIdx.x, role_a ? "second-pass" : "first-pass", role_a ? row - s.ring : row, ld_acquire(cur.flag), cur.target, ticket);
+                                    __trap();
+                                }
                             }
                         }
                         tma::fence_async_all();
                     }
                 }
+                cur = nxt;
                 // the buffer: the store of tile t - 3 has read it
                 const int b = (int)(t % TMA_BUFFERS);
                 if (t >= TMA_BUFFERS) tma::mbar_wait(&sm.empty[b], (t / TMA_BUFFERS - 1) & 1, "loader: empty");

@@ -1,0 +1,8 @@
+#!/bin/bash
+# quick look at the TMA-fed two-pass launch: parity + GB/s at the given lengths, then the pass-through pipeline alone
+# usage: tools/quick_tma.sh tag [lg ...]       (environment knobs are passed through)
+tag=$1; shift
+lgs=${@:-15 16 17 18 19 20}
+export DSC_NO_CLUSTER=${DSC_NO_CLUSTER-1}
+(timeout 300 python tools/check_tma.py 0 $lgs 2>&1; echo "rc=$?") | grep "rows=[0-9][0-9][0-9]\|rc=\|FAILED\|stuck" | sed "s/^/$tag /"
+for lg in 16 18 20; do DSC_TMA_DEBUG_SKIP=1 timeout 60 python tools/check_tma.py 0 $lg 2>&1 | grep "rows=[0-9][0-9][0-9]" | sed "s/^/$tag skip=1 /"; done
