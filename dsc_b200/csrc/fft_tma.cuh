@@ -6,7 +6,7 @@
 // DRAM / L2 latency (ncu: no unit above 40 %, stalls spread over load-queue throttling and payload latency).
 // Here the payload travels by bulk tensor copies (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) between
 // memory and three 64 KiB shared-memory buffers, signalled through mbarriers; the butterfly warps only ever
-// touch shared memory and registers, and one producer warp keeps loads and stores in flight around them.
+// touch shared memory and registers; a loader thread and one storer thread per buffer keep loads and stores in flight.
 //
 //   n = n1 * n2, row x[i1][q] (i1 < n1 stride n2), result X[k1 + n1 k2] = out[k2][k1]
 //

@@ -7,7 +7,12 @@
 // with three 64 KiB buffers per SM and one issuing thread (the loader + storer of four_step_tma merged; no row counters:
 // the contents do not matter here).  Per point: 8 B DRAM -> L2 -> SM, 8 B SM -> L2, 8 B L2 -> SM, 8 B SM -> L2 -> DRAM --
 // twice the L2 trips of a plain copy for the same 16 algorithmic bytes.  Printed: algorithmic GB/s (16 B per point), to be
-// read next to tma_tile_copy's 6.5 - 6.8 TB/s for the one-pass copy of the same boxes.
+// read next to tma_tile_copy's 6.5 - 6.8 TB/s for the one-pass copy of the same boxes, and the cycles a tile spends between
+// the issue of its load and its landing / in the store's read of the buffer.
+// Measured on B200 (profiles/r2b_two_pass_copy.log): 4.7 - 4.8 TB/s when the second pass reads rows written >= 48 rows
+// (24 MB) earlier, 3.1 - 3.4 TB/s when its reads chase the first pass's writes by 16 - 24 rows; first pass alone 8.6 - 8.9
+// TB/s read+write.  L2 moves 3 x 8 B per point and direction here against 2 x 8 B in a one-pass copy: ~14 TB/s either way.
+// usage: two_pass_copy [ring_mb:lag_rows:discard:wpol:rpol ...]
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I dsc_b200/csrc -I include -o tools/micro/two_pass_copy tools/micro/two_pass_copy.cu
 #include <cstdio>
 #include <cstdlib>
@@ -147,13 +152,12 @@ int main(int argc, char **argv) {
     }
     if (n_cases == 0) {
         const Case dflt[] = {
-            {64, 16, 1, 0, 0, 1, 0, "both passes, 64 MB ring, lag 16 rows, discard"},
-            {64, 16, 0, 0, 0, 1, 0, "both passes, 64 MB ring, lag 16 rows, no discard"},
-            {64, 4, 1, 0, 0, 1, 0, "both passes, 64 MB ring, lag 4 rows, discard"},
-            {32, 8, 1, 0, 0, 1, 0, "both passes, 32 MB ring, lag 8 rows, discard"},
-            {128, 32, 1, 0, 0, 1, 0, "both passes, 128 MB ring, lag 32 rows, discard"},
+            {64, 48, 1, 0, 0, 1, 0, "both passes, 64 MB ring, reads 48 rows behind, discard"},
+            {64, 48, 0, 0, 0, 1, 0, "both passes, 64 MB ring, reads 48 rows behind, no discard"},
+            {128, 64, 1, 0, 0, 1, 0, "both passes, 128 MB ring, reads 64 rows behind, discard"},
+            {64, 20, 1, 0, 0, 1, 0, "both passes, reads 20 rows behind (chasing the writes)"},
             {64, 16, 1, 0, 1, 1, 0, "first pass alone (DRAM -> L2 ring)"},
-            {64, 16, 1, 1, 0, 1, 0, "second pass alone (L2 ring -> DRAM)"},
+            {64, 16, 1, 1, 0, 1, 0, "second pass alone (stale ring -> DRAM)"},
         };
         for (const Case &c : dflt) cases[n_cases++] = c;
     }
