@@ -658,10 +658,14 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
     FusedEntry *fe = fused_entry<T, FWD>(p->lg_n1, p->lg_n2);
     const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
 #if !defined(DSC_EMUL)
-    // 16 points per thread (register-direct, four blocks per SM): dense complex rows only
-    static const bool want_f16 = [] { const char *e = getenv("DSC_FUSED_E16"); return e != nullptr && *e == '1'; }();
+    // 16 points per thread (64 registers, four 256-thread blocks per SM instead of two): dense complex rows, whole or in
+    // segments of at least one thread step.  Measured on B200 against 32 points per thread: 2698 -> 3156 GB/s at 2^15 and
+    // 2825 -> 3174 at 2^16, but 2780 -> 2715 at 2^17 and 2791 -> 2488 at 2^18 (a 512-point pass then needs a second exchange):
+    // default for passes of at most 256 points; DSC_FUSED_E16=0 / 1 forces it off / on wherever the tables exist.
+    static const int f16_env = [] { const char *e = getenv("DSC_FUSED_E16"); return e == nullptr || *e == '\0' ? -1 : atoi(e); }();
+    const bool want_f16 = f16_env < 0 ? (p->lg_n1 <= 8 && p->lg_n2 <= 8) : f16_env != 0;
     if (want_f16 && fe != nullptr && fe->fn16 != nullptr && p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr &&
-        first.in_kind == IN_COMPLEX && first.in_limit >= n && first.seg_shift == 0 &&
+        first.in_kind == IN_COMPLEX && first.in_limit >= n && (first.seg_shift == 0 || first.seg_shift >= p->lg_n - 4) &&
         rows * (n2 / fe->lpb_a16 + n1 / fe->lpb_b16) < 0x7fffffffLL && work != nullptr && work_bytes >= sync_bytes + row_bytes) {
         set_stage_tables<T>(a, p->tw1_e16);
         set_stage_tables<T>(b, p->tw2_e16);

@@ -6,7 +6,8 @@
                 that has the tables (default only for passes of at most 256 points)
    tma-e32      ... with 32 points per thread on 64 KiB tiles everywhere
    tma-direct   finished tiles stored from the registers, buffers released after the last exchange (opt-in variant)
-   registers-e16  the register-direct launch with 16 points per thread, four blocks per SM (opt-in variant)
+   registers-e16  the register-direct launch with 16 points per thread, four blocks per SM, for every pair of passes that
+                has the tables (default only for passes of at most 256 points); "registers" forces 32 points
    real-sweep   packed-real transforms with the bin-pair step as a separate sweep instead of fused into the TMA-fed launch
    real-fused-f32  the float32 filter through the fused launch too (default for float64 only: slower for float32)
 The selection is made through environment variables the library reads once, hence one subprocess per variant."""
@@ -24,7 +25,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("name,env", [("default", {}), ("clusters", {"DSC_CLUSTER_LGS": "14,15,16,17"}),
                                       ("clusters-unpipelined", {"DSC_CLUSTER_LGS": "14,15,16,17", "DSC_CLUSTER_PIPE": "0"}),
-                                      ("registers", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1"}),
+                                      ("registers", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1", "DSC_FUSED_E16": "0"}),
                                       ("tma-e16", {"DSC_TMA_E16": "1", "DSC_NO_CLUSTER": "1"}),
                                       ("tma-e32", {"DSC_TMA_E16": "0", "DSC_NO_CLUSTER": "1"}),
                                       ("tma-direct", {"DSC_TMA_DIRECT": "1", "DSC_TMA_E16": "0", "DSC_NO_CLUSTER": "1"}),
