@@ -240,20 +240,25 @@ def ncu_traffic_per_launch():
 
 
 def two_pass_copy_ceiling():
-    """What the memory system alone allows a two-pass transform on this GPU: tools/micro/two_pass_copy (built by
-    __graft_entry__.build()) moves the tiles of the TMA-fed four-step launch at 2^16 points per row -- box load, work row in
-    an L2-resident ring, box store -- with no arithmetic and no row counters.  None when the binary is missing."""
-    exe = os.path.join(ROOT, "tools", "micro", "two_pass_copy")
-    if not os.path.isfile(exe):
-        return None
-    try:
-        out = subprocess.run([exe, "64:48:1:1:0"], capture_output=True, text=True, timeout=120).stdout
-        gbs = float(out.split("GB/s")[0].split()[-1])
-    except Exception:      # noqa: BLE001  (an auxiliary figure must not lose the bench line)
-        return None
-    return {"gbs": gbs, "unit": "GB/s algorithmic (16 B per point)",
-            "how": "tools/micro/two_pass_copy 64:48:1:1:0: 64 KiB tiles, three buffers per SM, 64 MB work-row ring read 48 rows "
-                   "behind its writes, consumed lines discarded from L2; data movement only"}
+    """What the memory system alone allows a two-pass transform on this GPU: tools/micro/two_pass_copy* (built by
+    __graft_entry__.build()) move the tiles of the TMA-fed four-step launch -- box load, work row in an L2-resident ring,
+    box store; rows of 2^16 / 2^18 / 2^20 points, i.e. box rows of 256 / 128 / 64 bytes -- with no arithmetic and no row
+    counters.  None when the binaries are missing."""
+    res = {}
+    for lg, exe_name, case in ((16, "two_pass_copy", "64:48:1:1:0"), (18, "two_pass_copy_n512", "64:16:1:1:0"),
+                               (20, "two_pass_copy_n1024", "64:4:1:1:0")):
+        exe = os.path.join(ROOT, "tools", "micro", exe_name)
+        if not os.path.isfile(exe):
+            return None
+        try:
+            out = subprocess.run([exe, case], capture_output=True, text=True, timeout=120).stdout
+            res[lg] = float(out.split("GB/s")[0].split()[-1])
+        except Exception:      # noqa: BLE001  (an auxiliary figure must not lose the bench line)
+            return None
+    return {"gbs_by_lg_n": res, "unit": "GB/s algorithmic (16 B per point)",
+            "how": "tools/micro/two_pass_copy{,_n512,_n1024} ring_mb:lag_rows:discard = 64:48:1 / 64:16:1 / 64:4:1: 64 KiB tiles, three "
+                   "buffers per SM, 64 MB work-row ring read 24 - 32 MB behind its writes, consumed lines discarded from L2 "
+                   "(not the 64-byte rows of 2^20); data movement only; 2^15 / 2^17 / 2^19 are compared with the next larger geometry"}
 
 
 def rel_l2(a, b):
@@ -665,7 +670,7 @@ def run_ours(args, rank, world, local_rank):
         if ceiling:
             for p in sweep:
                 if p["lg_n"] >= 15:       # lengths beyond one shared-memory pass: two trips through L2 per point
-                    p["frac_of_two_pass_copy"] = p["algorithmic_gbs"] / ceiling["gbs"]
+                    p["frac_of_two_pass_copy"] = p["algorithmic_gbs"] / ceiling["gbs_by_lg_n"][p["lg_n"] + p["lg_n"] % 2]
         configs.append({"config": "sweep", "workload": "complex64 fft+ifft, last axis, 2^27 points per tensor (1 GiB), N = 2^10 .. 2^20",
                         "tolerance": 1e-5, "target_frac": 0.70, "points": sweep, "two_pass_copy_ceiling": ceiling,
                         "min_frac": min(p["frac"] for p in sweep), "max_rel_l2_vs_oracle": max(p["rel_l2_vs_oracle"] for p in sweep)})

@@ -22,8 +22,19 @@
 
 using namespace dscfft;
 
-constexpr int TILE = 64 * 1024, NBUF = 3;
-constexpr int N1 = 256, N2 = 256, L = 32;             // 2^16-point rows: 8 A tiles + 8 B tiles per row
+#ifndef TPC_TILE_KB
+#define TPC_TILE_KB 64
+#endif
+#ifndef TPC_NBUF
+#define TPC_NBUF 3
+#endif
+constexpr int TILE = TPC_TILE_KB * 1024, NBUF = TPC_NBUF;          // -DTPC_TILE_KB=32 -DTPC_NBUF=6: the 16-point variant's tiles
+#ifndef TPC_N
+#define TPC_N 256
+#endif
+// rows of TPC_N x TPC_N points (2^16 / 2^18 / 2^20): N2 / L first-pass + N2 / L second-pass tiles per row, box rows of L x 8 bytes
+constexpr int N1 = TPC_N, N2 = TPC_N, L = TILE / (N1 * 8);
+constexpr int BOX = N1 < 256 ? N1 : 256;                // box extents are at most 256
 constexpr int TILES_PER_ROW = N2 / L;
 
 __global__ void __launch_bounds__(64, 1)
@@ -65,8 +76,10 @@ two_pass_copy(const __grid_constant__ CUtensorMap in, const __grid_constant__ CU
         t_issue[b] = clock64();
         if (lane != 0) return;
         tma::mbar_arrive_expect_tx(&full[b], TILE);
-        if (d.role_a) tma::load_3d(buf + b * TILE, &in, d.r * L, 0, d.row, &full[b], pol_stream);
-        else tma::load_3d(buf + b * TILE, &wk, d.r * L, 0, d.row % ring_rows, &full[b], pol_r);
+        for (int r0 = 0; r0 < N1; r0 += BOX) {
+            if (d.role_a) tma::load_3d(buf + b * TILE + (size_t)r0 * L * 8, &in, d.r * L, r0, d.row, &full[b], pol_stream);
+            else tma::load_3d(buf + b * TILE + (size_t)r0 * L * 8, &wk, d.r * L, r0, d.row % ring_rows, &full[b], pol_r);
+        }
     };
     auto next_live = [&](Desc &d) {
         for (;;) {
@@ -93,14 +106,16 @@ two_pass_copy(const __grid_constant__ CUtensorMap in, const __grid_constant__ CU
             unsigned char *dst = work + ((size_t)(m.row % ring_rows) * TILES_PER_ROW + m.r) * TILE;
             if (lane == 0) tma::store_linear(dst, buf + b * TILE, TILE, pol_w);
         } else {
-            if (discard) {
+            if (discard && L * 8 >= 128) {       // narrower rows share their 128-byte lines with the neighbouring tile
                 const unsigned char *base = work + (size_t)(m.row % ring_rows) * TILES_PER_ROW * TILE + (size_t)m.r * L * 8;
-                for (int i = lane; i < N2 * 2; i += 32) {
-                    const unsigned char *p = base + (size_t)(i / 2) * N1 * 8 + (i % 2) * 128;
+                constexpr int PER_ROW = L * 8 >= 128 ? L * 8 / 128 : 1;
+                for (int i = lane; i < N2 * PER_ROW; i += 32) {
+                    const unsigned char *p = base + (size_t)(i / PER_ROW) * N1 * 8 + (i % PER_ROW) * 128;
                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
                 }
             }
-            if (lane == 0) tma::store_3d(&out, m.r * L, 0, m.row, buf + b * TILE, pol_stream);
+            if (lane == 0)
+                for (int r0 = 0; r0 < N2; r0 += BOX) tma::store_3d(&out, m.r * L, r0, m.row, buf + b * TILE + (size_t)r0 * L * 8, pol_stream);
         }
         const long long t_st = clock64();
         if (lane == 0) { tma::store_commit(); tma::store_wait_read(); }
@@ -135,7 +150,7 @@ int main(int argc, char **argv) {
         // rows of [256][256] 8-byte elements: box = [256 positions][32 columns]
         const cuuint64_t dims[3] = {(cuuint64_t)N2, (cuuint64_t)N1, (cuuint64_t)nrows};
         const cuuint64_t strides[2] = {(cuuint64_t)N2 * 8, (cuuint64_t)row_bytes};
-        const cuuint32_t box[3] = {L, 256, 1};
+        const cuuint32_t box[3] = {L, BOX, 1};
         const cuuint32_t es[3] = {1, 1, 1};
         return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
