@@ -270,6 +270,9 @@ struct ColumnsEntry {
     int lg_n1, lg_n2, threads, l_a, l_b, smem;
     int grid;
     bool configured;
+    // float passes of at most 256 points: 16 points per thread, four 256-thread blocks per SM (like FusedEntry::fn16)
+    void (*fn16)(const FftArgs, const FftArgs, const FourStepSync, const ColumnsGeom);
+    int l_a16, l_b16, smem16, grid16;
 };
 
 template <typename T, bool FWD, int LG_N1, int LG_N2, int THREADS = fused_threads<T>(LG_N1, LG_N2)>
@@ -282,6 +285,12 @@ ColumnsEntry make_columns() {
     e.smem = fused_smem_bytes<T, LG_N1, LG_N2, THREADS>();
     e.grid = 0;
     e.configured = false;
+    e.fn16 = nullptr; e.l_a16 = e.l_b16 = e.smem16 = e.grid16 = 0;
+    if constexpr (sizeof(T) == 4 && LG_N1 <= 8 && LG_N2 <= 8 && LG_N2 >= 7 && THREADS == 256) {
+        e.fn16 = four_step_columns<T, LG_N1, LG_N2, THREADS, FWD, 4>;
+        e.l_a16 = THREADS >> (LG_N1 - 4); e.l_b16 = THREADS >> (LG_N2 - 4);
+        e.smem16 = fused_smem_bytes<T, LG_N1, LG_N2, THREADS, 4>();
+    }
     return e;
 }
 

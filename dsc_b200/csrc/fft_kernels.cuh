@@ -1148,12 +1148,12 @@ DSC_DEV void column_tile(const FftArgs &a, const ColumnsGeom &g, const unsigned 
     }
 }
 
-template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+template <typename T, int LG_N1, int LG_N2, int THREADS, bool FWD, int LGE = 0>
+__global__ void __launch_bounds__(THREADS, (LGE > 0 && LGE < (sizeof(T) == 4 ? 5 : 4) ? 1024 : 512) / THREADS)
 four_step_columns(const FftArgs a, const FftArgs b, const FourStepSync s, const ColumnsGeom g) {
-    constexpr int LG_E1 = pass_lg_e<T>(LG_N1, LG_N2), LG_E2 = pass_lg_e<T>(LG_N2, LG_N1);
+    constexpr int LG_E1 = fused_lg_e<T>(LGE, LG_N1, LG_N2), LG_E2 = fused_lg_e<T>(LGE, LG_N2, LG_N1);
     constexpr int L_A = THREADS >> (LG_N1 - LG_E1), L_B = THREADS >> (LG_N2 - LG_E2);
-    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS>();
+    constexpr int TABLE_AT = fused_table_at<T, LG_N1, LG_N2, THREADS, LGE>();
     DSC_DYN_SMEM(smem_raw);
     run_tickets(s,
         [&](unsigned row, unsigned r, int par, auto &before_scatter) {

@@ -826,34 +826,45 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     ColumnsEntry *ce = p->col_lg_n2 ? columns_entry<T, FWD>(p->col_lg_n1, p->col_lg_n2) : nullptr;
     const int lg_inner = pow2_shift(inner);
     if (ce == nullptr || lg_inner < 0) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis of inner extent %lld", n, inner);
-    const int l_max = ce->l_a > ce->l_b ? ce->l_a : ce->l_b;
+    // 16 points per thread where the plan's column tables are its two-pass tables and carry the 16-point copies (passes of at
+    // most 256 points): twice the resident warps, like the last-axis register-direct launch.  DSC_COLUMNS_E16=0 disables.
+    bool e16 = false;
+#if !defined(DSC_EMUL)
+    static const bool no_c16 = [] { const char *e = getenv("DSC_COLUMNS_E16"); return e != nullptr && *e == '0'; }();
+    e16 = !no_c16 && ce->fn16 != nullptr && p->lg_n2 != 0 && p->col_lg_n1 == p->lg_n1 && p->col_lg_n2 == p->lg_n2 &&
+          p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr;
+#endif
+    const int ce_l_a = e16 ? ce->l_a16 : ce->l_a, ce_l_b = e16 ? ce->l_b16 : ce->l_b, ce_smem = e16 ? ce->smem16 : ce->smem;
+    auto ce_fn = e16 ? ce->fn16 : ce->fn;
+    const int l_max = ce_l_a > ce_l_b ? ce_l_a : ce_l_b;
     if (inner < l_max) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld): inner extent %lld is narrower than a tile", n, inner);
     const int lg_ic = columns_chunk_lg(n, lg_inner, l_max, sizeof(V));
     const long long ic = 1LL << lg_ic, chunks = inner >> lg_ic, rows = outer * chunks;
     if (rows <= 0) return 0;
     const size_t row_bytes = (size_t)n * (size_t)ic * sizeof(V);
     const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
-    const long long tiles_a = (1LL << p->col_lg_n2) * (ic / ce->l_a), tiles_b = (1LL << p->col_lg_n1) * (ic / ce->l_b);
+    const long long tiles_a = (1LL << p->col_lg_n2) * (ic / ce_l_a), tiles_b = (1LL << p->col_lg_n1) * (ic / ce_l_b);
     if (work == nullptr || work_bytes < sync_bytes + row_bytes || rows * (tiles_a + tiles_b) >= 0x7fffffffLL ||
         outer * chunks > 0x7fffffffLL)
         return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis: work buffer of %zu bytes holds no row of %zu", n, work_bytes, row_bytes);
 #if defined(DSC_EMUL)
     ce->grid = 3;
 #else
-    if (!ce->configured) {
-        if (ce->smem > 48 * 1024) {
-            const cudaError_t err = cudaFuncSetAttribute((const void *)ce->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce->smem);
+    if (e16 ? ce->grid16 == 0 : !ce->configured) {
+        if (ce_smem > 48 * 1024) {
+            const cudaError_t err = cudaFuncSetAttribute((const void *)ce_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce_smem);
             if (err != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "smem attribute: %s", cudaGetErrorString(err));
         }
         int per_sm = 0, dev = 0, sms = 0;
-        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ce->fn, ce->threads, ce->smem);
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ce_fn, ce->threads, ce_smem);
         if (err == cudaSuccess) err = cudaGetDevice(&dev);
         if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (err != cudaSuccess || per_sm < 1) return fail(DSC_CUDA_ELAUNCH, "occupancy query: %s", cudaGetErrorString(err));
-        ce->grid = per_sm * sms;
-        ce->configured = true;
+        if (e16) ce->grid16 = per_sm * sms;
+        else { ce->grid = per_sm * sms; ce->configured = true; }
     }
 #endif
+    const int ce_grid = e16 ? ce->grid16 : ce->grid;
     long long ring = (long long)((work_bytes - sync_bytes) / row_bytes);
     const long long cap = (long long)(((size_t)64 << 20) / row_bytes) > 4 ? (long long)(((size_t)64 << 20) / row_bytes) : 4;
     if (ring > cap) ring = cap;
@@ -866,7 +877,7 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     s.tiles_b = (int)tiles_b;
     s.ring = (int)ring;
     s.rows = (int)rows;
-    long long lag = (3LL * ce->grid + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
+    long long lag = (3LL * ce_grid + tiles_a + tiles_b - 1) / (tiles_a + tiles_b);
     if (lag < 1) lag = 1;
     // at most half the ring -- with a ring of ONE work row that is lag 0 (second pass of row r ticketed before the
     // first pass of row r + 1): raising it back to 1 would ticket A(r + 1) ahead of the B(r) it has to wait for,
@@ -878,11 +889,11 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     V *mid = (V *)((char *)work + sync_bytes);
     FftArgs a{}, b{};
     a.x = x; a.out = mid; a.ring_out = ring;
-    set_stage_tables<T>(a, p->col_tw1);
+    set_stage_tables<T>(a, e16 ? p->tw1_e16 : p->col_tw1);
     a.tw_lo = p->col_lo; a.tw_hi = p->col_hi;
     a.four_shift = p->col_shift; a.four_mask = (1 << p->col_shift) - 1;
     b.x = mid; b.out = out; b.ring_in = ring;
-    set_stage_tables<T>(b, p->col_tw2);
+    set_stage_tables<T>(b, e16 ? p->tw2_e16 : p->col_tw2);
     b.do_scale = !FWD; b.scale = 1.0 / (double)n;
     ColumnsGeom g{};
     g.x_ostride = (long long)x_n * inner;
@@ -911,8 +922,8 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
 #endif
     const long long tiles = rows * (tiles_a + tiles_b);
-    const unsigned blocks = (unsigned)(tiles < ce->grid ? tiles : ce->grid);
-    DSC_LAUNCH(ce->fn, blocks, ce->threads, ce->smem, stream, a, b, s, g);
+    const unsigned blocks = (unsigned)(tiles < ce_grid ? tiles : ce_grid);
+    DSC_LAUNCH(ce_fn, blocks, ce->threads, ce_smem, stream, a, b, s, g);
     return check_launch("four_step_columns");
 }
 
