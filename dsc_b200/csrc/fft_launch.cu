@@ -441,8 +441,10 @@ int four_step_tma_launch(const dsc_cuda_plan *p, const FftArgs &first, long long
         a.filt = rf->filt;
         a.in = first.x; a.in_pitch = first.gi.ostride;
     }
+#if defined(DSC_TMA_EXPERIMENTS)
     static const int debug_skip = [] { const char *e = getenv("DSC_TMA_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
     a.debug_skip = debug_skip;
+#endif
     static const bool want_direct = [] { const char *e = getenv("DSC_TMA_DIRECT"); return e != nullptr && *e == '1'; }();
     const bool direct = want_direct && rf == nullptr && !e16 && te->fn_direct != nullptr;
     const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);

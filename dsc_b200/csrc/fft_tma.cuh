@@ -177,8 +177,8 @@ struct TmaArgs {
     const void *in;                // REAL == 2: the bin rows X[0..n] (for the one column no box load covers)
     long long in_pitch;
     int prefetch;                  // first-pass boxes are prefetched into L2 when their ticket is taken, two tiles ahead
-    int debug_skip;                // timing experiments only (wrong results): 1 = tiles pass through untouched, 2 = only the
-                                   // shared-memory traffic of a tile (two round trips per point), no arithmetic
+    int debug_skip;                // builds with DSC_TMA_EXPERIMENTS only (wrong results): 1 = tiles pass through untouched,
+                                   // 2 = only the shared-memory traffic of a tile (two round trips per point), no arithmetic
 };
 
 struct TmaTileDesc { unsigned role_a, row, r, exit; };
@@ -938,6 +938,8 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if constexpr (REAL == 2) {
             if (d.role_a) tma_mix_tile<T, LG_N1, LG_N2, L_A>(buf, a, d.r, gtid, bar_id, xm_a, xm_b);
         }
+#if defined(DSC_TMA_EXPERIMENTS)
+        // timing experiments of DESIGN.md 4a (make DSC_TMA_EXPERIMENTS=1): the product library has no such switch
         if (!DIRECT && REAL == 0 && a.debug_skip != 0) {
             if (a.debug_skip == 2) {
                 volatile V *vb = buf;
@@ -958,6 +960,7 @@ four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             if ((tid & 31) == 0) tma::mbar_arrive(&sm.ready[b]);
             continue;
         }
+#endif
         if constexpr (DIRECT) {
             if (d.role_a) {
                 // this thread's run of the work line W[q0 + l_last][j_last + c TT]

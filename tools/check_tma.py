@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dsc_b200 import cuda_api
 
-api = cuda_api.CudaApi()
+api = cuda_api.CudaApi(os.path.abspath(os.environ["DSC_LIB"])) if os.environ.get("DSC_LIB") else cuda_api.CudaApi()
 dev = torch.device("cuda:0")
 
 
