@@ -21,6 +21,9 @@ struct KernelEntry {
     int threads;    // block size
     int smem;       // dynamic shared memory bytes
     bool configured;
+    // dense lines with one block per SM: persistent blocks that prefetch their next line into L2 (fft_lines_persist)
+    void (*fn_persist)(const FftArgs, const long long);
+    int grid_persist;
 };
 
 template <typename T> struct Tile;
@@ -66,6 +69,13 @@ KernelEntry make_entry() {
     e.threads = LPB * Sc::TT;
     e.smem = LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>), mode_is_dense(MODE) ? Sc::TT : 0) * (int)sizeof(cx<T>);
     e.configured = false;
+    e.fn_persist = nullptr;
+    e.grid_persist = 0;
+#if !defined(DSC_EMUL)
+    if constexpr ((MODE == MODE_FAST || MODE == MODE_R2C_FAST || MODE == MODE_C2R_FAST) &&
+                  LPB * Sc::line_stride(LPB, (int)sizeof(cx<T>), Sc::TT) * (int)sizeof(cx<T>) > 114 * 1024)
+        e.fn_persist = fft_lines_persist<T, LG_N, LG_E, LPB, FWD, MODE>;
+#endif
     return e;
 }
 

@@ -659,6 +659,32 @@ fft_lines(const FftArgs a) {
     fft_lines_body<T, LG_N, LG_E, LPB, FWD, MODE>(a, (long long)blockIdx.x, smem_raw);
 }
 
+#if !defined(DSC_EMUL)
+// Dense lines so long that ONE block fits an SM (float 2^14, double 2^13: 128 KiB of shared memory per line): with
+// one-shot blocks nothing overlaps a line's load with the line before it, and the load of 128 KiB from DRAM at one SM's
+// share of the bandwidth is a third of the line's time.  Persistent blocks (one per SM, lines blk, blk + grid, ...) ask L2
+// for their NEXT line (one cp.async.bulk.prefetch of the whole line) before they start on the current one: the DRAM
+// transfer then runs behind the transform and the line's loads are L2 hits.
+template <typename T, int LG_N, int LG_E, int LPB, bool FWD, int MODE>
+__global__ void __launch_bounds__(LPB * (1 << (LG_N - LG_E)), 1)
+fft_lines_persist(const FftArgs a, const long long blocks) {
+    DSC_DYN_SMEM(smem_raw);
+    // bytes of a block's input lines: N complex points (2N packed reals), or the N + 1 bins of an inverse real transform
+    constexpr size_t BYTES = (size_t)LPB * (size_t)((1 << LG_N) + (MODE == MODE_C2R_FAST ? 1 : 0)) * sizeof(cx<T>);
+    for (long long blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+        const long long nxt = blk + gridDim.x;
+        if (threadIdx.x == 0 && nxt < blocks) {
+            // whole 16-byte granules inside the line (rows of N + 1 complex64 bins start 8 bytes off every other line)
+            const unsigned long long lo = ((unsigned long long)a.x + (size_t)nxt * BYTES + 15) & ~15ULL;
+            const unsigned long long hi = ((unsigned long long)a.x + (size_t)(nxt + 1) * BYTES) & ~15ULL;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+        }
+        fft_lines_body<T, LG_N, LG_E, LPB, FWD, MODE>(a, blk, smem_raw);
+        __syncthreads();            // the next line's first exchange reuses the buffers
+    }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // Register-direct tiles for the two passes of the four-step transform.
 //

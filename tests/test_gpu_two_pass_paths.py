@@ -10,6 +10,8 @@
                 has the tables (default only for passes of at most 256 points); "registers" forces 32 points
    real-sweep   packed-real transforms with the bin-pair step as a separate sweep instead of fused into the TMA-fed launch
    real-fused-f32  the float32 filter through the fused launch too (default for float64 only: slower for float32)
+   one-shot     the longest single-pass lines (one block per SM) as one-shot blocks instead of persistent blocks with an
+                L2 prefetch of their next line
 The selection is made through environment variables the library reads once, hence one subprocess per variant."""
 import os
 import subprocess
@@ -30,12 +32,13 @@ pytestmark = pytest.mark.gpu
                                       ("tma-e32", {"DSC_TMA_E16": "0", "DSC_NO_CLUSTER": "1"}),
                                       ("tma-direct", {"DSC_TMA_DIRECT": "1", "DSC_TMA_E16": "0", "DSC_NO_CLUSTER": "1"}),
                                       ("registers-e16", {"DSC_NO_TMA": "1", "DSC_NO_CLUSTER": "1", "DSC_FUSED_E16": "1"}),
+                                      ("one-shot", {"DSC_NO_PERSIST": "1"}),
                                       ("real-sweep", {"DSC_NO_REAL_FUSE": "1"}),
                                       ("real-fused-f32", {"DSC_REAL_FUSE_F32": "1"})])
 def test_two_pass_paths(name, env):
     e = dict(os.environ)
     for k in ("DSC_NO_TMA", "DSC_NO_CLUSTER", "DSC_CLUSTER_LGS", "DSC_TMA_E16", "DSC_CLUSTER_PIPE", "DSC_NO_REAL_FUSE", "DSC_REAL_FUSE_F32",
-              "DSC_TMA_DIRECT", "DSC_FUSED_E16", "DSC_TMA_DEBUG_SKIP", "DSC_TMA_LAG"):
+              "DSC_TMA_DIRECT", "DSC_FUSED_E16", "DSC_TMA_DEBUG_SKIP", "DSC_TMA_LAG", "DSC_NO_PERSIST", "DSC_COLUMNS_E16"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, WORKER], capture_output=True, text=True, timeout=600, env=e)

@@ -13,14 +13,17 @@ from tests.devfft import DevFFT  # noqa: E402
 from tests.util import randn, rel_l2  # noqa: E402
 
 TIGHT = {"complex64": 2e-6, "complex128": 5e-15}
-CASES = [("complex64", 14, 300), ("complex64", 15, 1500), ("complex64", 15, 1), ("complex64", 16, 9), ("complex64", 16, 700),
+# (2^14 complex64 / 2^13 complex128 and the real transforms of twice those lengths are the longest single-pass lines: one
+# block per SM, persistent blocks that prefetch their next line into L2 once there are more lines than SMs; DSC_NO_PERSIST=1
+# selects the one-shot launch)
+CASES = [("complex64", 14, 300), ("complex128", 13, 300), ("complex64", 15, 1500), ("complex64", 15, 1), ("complex64", 16, 9), ("complex64", 16, 700),
          ("complex64", 17, 3), ("complex64", 17, 300), ("complex64", 18, 5), ("complex64", 19, 3), ("complex64", 20, 3),
          ("complex64", 20, 40), ("complex128", 14, 1100), ("complex128", 15, 2), ("complex128", 16, 70), ("complex128", 17, 3),
          ("complex128", 18, 2), ("complex128", 19, 2)]
 # packed-real transforms of two-pass orders: (real dtype, log2 of the real length, rows).  float64 rows run with the bin-pair
 # step fused into the TMA-fed launch (DSC_NO_REAL_FUSE=1: the separate sweep); float32 rfft rows have an odd pitch and keep
 # the sweep, the float32 filter is fused up to 2^20 samples
-REAL_CASES = [("float64", 15, 300), ("float64", 15, 1), ("float64", 16, 2), ("float64", 17, 70), ("float64", 18, 3), ("float64", 18, 41),
+REAL_CASES = [("float32", 15, 300), ("float64", 14, 300), ("float64", 15, 300), ("float64", 15, 1), ("float64", 16, 2), ("float64", 17, 70), ("float64", 18, 3), ("float64", 18, 41),
               ("float64", 19, 2), ("float32", 16, 5), ("float32", 18, 3), ("float32", 20, 2)]
 FILTER_CASES = [("float32", 16, 1), ("float32", 16, 300), ("float32", 17, 3), ("float32", 18, 70), ("float32", 19, 2), ("float32", 20, 37),
                 ("float32", 21, 2), ("float64", 16, 3), ("float64", 18, 35), ("float64", 19, 2)]

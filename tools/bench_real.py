@@ -44,6 +44,9 @@ def run(lg_real, prec=0, total_bytes=1 << 30):
           f"irfft {t_i:.3f} ms {nbytes / t_i / 1e6:.0f} GB/s | roundtrip {err:.1e}", flush=True)
 
 
+if __name__ != "__main__":          # tools/bench_real_ab.py: the one-block-per-SM lengths only
+    run(14); run(15); run(13, 1); run(14, 1)
+    sys.exit(0)
 for lg in (8, 10, 11, 12, 13, 14, 15, 16, 18, 20):
     run(lg)
 for lg in (10, 12, 13, 14, 16, 18):
