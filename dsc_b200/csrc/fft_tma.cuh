@@ -648,29 +648,29 @@ DSC_DEV void tma_mix_tile(cx<T> *buf, const TmaArgs &a, const unsigned u, const 
 }
 
 // ---- the persistent launch --------------------------------------------------------------------------------
-// One block per SM: warps 0..15 are two butterfly groups, lane 0 of warp 16 is the loader, lane 0 of warp 17 the
-// storer.  The block's tile sequence is t = 0, 1, 2, ...: tile t is transformed by group t % 2 in buffer t % 3.
-//   loader, tile t   :  take a ticket -> wait for the tile's dependency (all first-pass tiles of the row; the second
-//                       pass of the row that used the work row before) -> wait empty[t % 3] (the store of tile t - 3 has
-//                       read the buffer) -> descriptor + box loads, completion on full[t % 3].
-//   group, tile t    :  wait full[t % 3] -> transform in place -> fence.proxy.async -> arrive on ready[t % 3].
-//   storer, tile t   :  wait ready[t % 3] -> bulk store -> wait until it has READ the buffer -> arrive on empty[t % 3]
-//                       -> once the store before it has COMPLETED, publish that tile's row counter.  Whenever the
-//                       next tile is not ready yet it first completes and publishes everything outstanding, so no
-//                       other block (or this block's loader) waits on a counter longer than a store takes.
+// One block per SM: warps 0..15 are two butterfly groups, lane 0 of warp 16 is the loader, lane 0 of warps 17..19 the
+// storers of buffers 0..2.  The block's tile sequence is t = 0, 1, 2, ...: tile t is transformed by group t % 2 in buffer
+// t % 3.
+//   loader, tile t   :  ticket and row counter looked up one tile ahead -> wait for the tile's dependency (all first-pass
+//                       tiles of the row; the second pass of the row that used the work row before) -> wait empty[t % 3]
+//                       (the store of tile t - 3 has read the buffer) -> descriptor + box loads, completion on full[t % 3].
+//   group, tile t    :  wait full[t % 3] -> transform in place -> fence.proxy.async -> one arrival per warp on ready[t % 3].
+//   storer t % 3     :  wait ready[t % 3] -> bulk store -> wait until it has READ the buffer -> arrive on empty[t % 3]
+//                       -> wait until it has COMPLETED -> proxy fence -> release-add on the tile's row counter.
+// The launch is paced by this copy pipeline (three buffers circulating between the copy engine and the groups), not by the
+// butterflies: DESIGN.md 4a, tools/micro/two_pass_copy.cu.
 // LGE / TILE: points per thread (log2) and bytes per tile.  The default (32 points, 64 KiB, one block per SM) leaves an SM
-// 16 butterfly warps at 96 registers, and in-kernel clocks show a group then needs ~10 000 cycles per tile: the transform,
-// not the data movement, paces the launch.  With 16 points per thread the registers allow twice the
-// warps, but two 512-thread groups plus the copy warps exceed the 1024-thread block limit; so the 16-point variant runs on
-// 32 KiB tiles (groups stay 256 threads) with TWO blocks per SM: 32 butterfly warps, six tiles in flight.  It covers float
-// passes of up to 512 points (32-byte rows beyond that).
+// 16 butterfly warps at 96 registers.  With 16 points per thread the registers allow twice the warps, but two 512-thread
+// groups plus the copy warps exceed the 1024-thread block limit; so the 16-point variant runs on 32 KiB tiles (groups stay
+// 256 threads) with TWO blocks per SM: 32 butterfly warps, six tiles in flight.  It is the default for float passes of at
+// most 256 points (a 512-point pass would need a second exchange, and its half-size tiles 64-byte rows).
 // REAL: 0 = complex rows; 1 = forward with the packed-real bin-pair step fused into the second pass (tma_unmix_tile);
 // 2 = inverse whose first pass builds the packed points from the bins of the real transform (tma_mix_tile).
-// DIRECT: finished tiles leave from the registers (coalesced st.global, runs of 64 - 256 bytes) instead of going back into
-// the buffer for a bulk store, and a tile gives its buffer back right after its last exchange.  A buffer is then held for
-// load + half a transform instead of load + transform + store, so with the same three buffers more loads are in flight --
-// bytes in flight per SM, not the butterflies, bound the bulk-store variant (one group delivers 87 - 105 % of two).  The
-// storer thread only publishes row counters (after every warp of the group has issued its stores).
+// DIRECT (opt-in, measured slower): finished tiles leave from the registers (coalesced st.global, runs of 64 - 256 bytes)
+// instead of going back into the buffer for a bulk store, and a tile gives its buffer back right after its last exchange: a
+// buffer is held for load + half a transform instead of load + transform + store, but the 32 STG.64 per thread cost the
+// load/store pipe more than the freed buffer time returns.  The storer of buffer 0 only publishes row counters (after
+// every warp of the group has issued its stores).
 template <typename T, int LG_N1, int LG_N2, bool FWD, int LGE = tma_lg_e<T>(), int TILE = TMA_TILE_BYTES, int REAL = 0, bool DIRECT = false>
 __global__ void __launch_bounds__(TMA4_THREADS, (TILE * 2 <= TMA_TILE_BYTES ? 2 : 1))
 four_step_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
