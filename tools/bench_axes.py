@@ -36,8 +36,12 @@ def run(outer, n, inner, prec=0, reps=5):
 
 
 if __name__ != "__main__":
-    for shape in [(1, 32768, 4096), (4, 65536, 512), (16, 32768, 256), (2, 65536, 1024)]:
+    for shape in ([(1, 4096, 32768), (32, 4096, 1024), (1, 1024, 131072), (128, 1024, 1024), (1, 2048, 65536)] if os.environ.get("AXES_SINGLE")
+                  else [(1, 32768, 4096), (4, 65536, 512), (16, 32768, 256), (2, 65536, 1024)]):
         run(*shape)
+    if os.environ.get("AXES_SINGLE"):
+        run(1, 4096, 16384, 1)
+        run(64, 1024, 1024, 1)
     sys.exit(0)
 for shape in [(1, 4096, 32768), (32, 4096, 1024), (1, 1024, 131072), (128, 1024, 1024), (2048, 256, 256),
               (1, 64, 2097152), (1, 8192, 16384), (1, 16384, 8192), (32768, 64, 64), (1048576, 16, 8), (4096, 4096, 3)]:
