@@ -681,7 +681,6 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
 
     FusedEntry *fe = fused_entry<T, FWD>(p->lg_n1, p->lg_n2);
     const size_t sync_bytes = align_up((size_t)(1 + 2 * rows) * sizeof(unsigned), 256);
-#if !defined(DSC_EMUL)
     // 16 points per thread (64 registers, four 256-thread blocks per SM instead of two): dense complex rows, whole or in
     // segments of at least one thread step.  Measured on B200 against 32 points per thread: 2698 -> 3156 GB/s at 2^15 and
     // 2825 -> 3174 at 2^16, but 2780 -> 2715 at 2^17 and 2791 -> 2488 at 2^18 (a 512-point pass then needs a second exchange):
@@ -698,6 +697,9 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         const long long cap = (long long)(l2_budget / row_bytes) > 4 ? (long long)(l2_budget / row_bytes) : 4;
         if (ring > cap) ring = cap;
         if (ring >= rows) ring = 0;
+#if defined(DSC_EMUL)
+        fe->grid16 = 3;
+#else
         if (fe->grid16 == 0) {
             if (fe->smem16 > 48 * 1024) {
                 const cudaError_t err = cudaFuncSetAttribute((const void *)fe->fn16, cudaFuncAttributeMaxDynamicSharedMemorySize, fe->smem16);
@@ -709,8 +711,8 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
             if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (err != cudaSuccess || per_sm < 1) return fail(DSC_CUDA_ELAUNCH, "occupancy query: %s", cudaGetErrorString(err));
             fe->grid16 = per_sm * sms;
-            if (getenv("DSC_DEBUG_OCC")) fprintf(stderr, "four_step_fused e16: %d blocks per SM, smem %d\n", per_sm, fe->smem16);
         }
+#endif
         FourStepSync s{};
         s.ticket = (unsigned *)work;
         s.a_done = s.ticket + 1;
@@ -730,14 +732,17 @@ int four_step(const dsc_cuda_plan *p, FftArgs first, long long rows, void *work,
         a.out = mid; a.lines = rows * n2; a.ring_out = ring; a.inner_shift = p->lg_n2;
         a.no_limit = 1;
         b.x = mid; b.out = dst; b.lines = rows * n1; b.ring_in = ring; b.inner_shift = p->lg_n1;
+#if defined(DSC_EMUL)
+        memset(work, 0, sync_bytes);
+#else
         const cudaError_t me = cudaMemsetAsync(work, 0, sync_bytes, (cudaStream_t)stream);
         if (me != cudaSuccess) return fail(DSC_CUDA_ELAUNCH, "memset: %s", cudaGetErrorString(me));
+#endif
         const long long tiles = rows * (s.tiles_a + s.tiles_b);
         const unsigned blocks = (unsigned)(tiles < fe->grid16 ? tiles : fe->grid16);
         DSC_LAUNCH(fe->fn16, blocks, fe->threads, fe->smem16, stream, a, b, s);
         return check_launch("four_step_fused e16");
     }
-#endif
     if (fe != nullptr && rows * (n2 / fe->lpb_a + n1 / fe->lpb_b) < 0x7fffffffLL &&
         work != nullptr && work_bytes >= sync_bytes + row_bytes) {
         // ring of work rows: as many as fit, but no more than keeps the intermediate inside L2
@@ -852,12 +857,9 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
     if (ce == nullptr || lg_inner < 0) return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis of inner extent %lld", n, inner);
     // 16 points per thread where the plan's column tables are its two-pass tables and carry the 16-point copies (passes of at
     // most 256 points): twice the resident warps, like the last-axis register-direct launch.  DSC_COLUMNS_E16=0 disables.
-    bool e16 = false;
-#if !defined(DSC_EMUL)
     static const bool no_c16 = [] { const char *e = getenv("DSC_COLUMNS_E16"); return e != nullptr && *e == '0'; }();
-    e16 = !no_c16 && ce->fn16 != nullptr && p->lg_n2 != 0 && p->col_lg_n1 == p->lg_n1 && p->col_lg_n2 == p->lg_n2 &&
-          p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr;
-#endif
+    const bool e16 = !no_c16 && ce->fn16 != nullptr && p->lg_n2 != 0 && p->col_lg_n1 == p->lg_n1 && p->col_lg_n2 == p->lg_n2 &&
+                     p->tw1_e16[1] != nullptr && p->tw2_e16[1] != nullptr;
     const int ce_l_a = e16 ? ce->l_a16 : ce->l_a, ce_l_b = e16 ? ce->l_b16 : ce->l_b, ce_smem = e16 ? ce->smem16 : ce->smem;
     auto ce_fn = e16 ? ce->fn16 : ce->fn;
     const int l_max = ce_l_a > ce_l_b ? ce_l_a : ce_l_b;
@@ -873,6 +875,7 @@ int four_step_columns_launch(const dsc_cuda_plan *p, const void *x, bool x_real,
         return fail(DSC_CUDA_EUNSUPPORTED, "two-pass transform (n=%lld) along a strided axis: work buffer of %zu bytes holds no row of %zu", n, work_bytes, row_bytes);
 #if defined(DSC_EMUL)
     ce->grid = 3;
+    ce->grid16 = 3;
 #else
     if (e16 ? ce->grid16 == 0 : !ce->configured) {
         if (ce_smem > 48 * 1024) {
